@@ -1,0 +1,105 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.json by running the UNMODIFIED
+reference (``/root/reference``, via ``oracle/ref_harness.py``).  Run in the build container:
+
+    python oracle/gen_golden.py
+
+Each case records a full FORK-mode episode of ``MComCore.step`` (reference
+``mobile_env/core/base.py:230-296``): positions, waypoint targets, SNR matrix,
+association, rounded pair rates, utilities, monitor scalars and ``time_is_up``.
+The notebook known-answer vectors (``mobile_env/GNN/GNN.ipynb`` cell 3 output raw 86-93,
+cell 17 output raw 723-1050) are asserted while generating so the fixtures are pinned
+to what the reference's authors saw.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+KAT1_BS = [(181, 153), (75, 68), (128, 32), (74, 108), (176, 115)]
+KAT1_POS = [(81, 109), (142, 187), (161, 86), (156, 91), (70, 21), (10, 48), (177, 108)]
+KAT1_RATES = {(1, 0): 0.84, (5, 1): 0.17, (4, 1): 0.57, (0, 3): 700.2, (2, 4): 1.33,
+              (6, 4): 233.4, (3, 4): 1.55}
+KAT2_BS = [(194, 153), (150, 104), (27, 70), (28, 186), (26, 127), (69, 172), (23, 140),
+           (189, 68), (63, 183), (31, 48)]
+KAT2_POS = [(65, 33), (54, 55), (33, 150), (97, 25), (36, 124), (54, 144), (43, 129)]
+# (ue, graph node, rate); graph node = 7 + bs_id
+KAT2_RATES = {(0, 9): 0.86, (1, 9): 3.74, (2, 6): 33.7, (3, 9): 0.1, (4, 4): 93.91,
+              (5, 6): 2.31, (6, 4): 17.68}
+
+KAT_CFG = {"ue": {"velocity": 10, "height": 1.8}, "bs": {"tx": 30}}
+
+
+def ep_cfg(n, extra=None):
+    cfg = {"EP_MAX_TIME": n, "arrival_params": {"ep_time": n}}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+CASES = {
+    # name: (bs_xy, num_ues, config, steps)
+    "kat1": (KAT1_BS, 7, KAT_CFG, 20),
+    "kat2": (KAT2_BS, 7, KAT_CFG, 20),
+    "default_v10": ([(40, 150), (100, 100), (160, 40), (30, 30), (170, 170), (100, 20), (20, 100), (150, 110)],
+                    7, {"ue": {"velocity": 10}}, 20),
+    "small_v1p5": ([(110, 130), (65, 80), (120, 30)], 5, ep_cfg(60), 60),
+    "medium_v1p5": ([(50, 50), (150, 50), (50, 150), (150, 150)], 15, ep_cfg(40), 40),
+    "medium_v3": ([(50, 50), (150, 50), (50, 150), (150, 150)], 15, ep_cfg(40, {"ue": {"velocity": 3}}), 40),
+    "large_v5": ([(20 + 45 * (i % 4), 25 + 50 * (i // 4)) for i in range(13)], 30,
+                 ep_cfg(30, {"ue": {"velocity": 5}}), 30),
+    # UE0 of the seed-2028 trajectory stands exactly on a BS at step 0 (d = 0 => log10(1e-16))
+    "ue_on_bs": ([(81, 109), (142, 187), (10, 10)], 7, {"ue": {"velocity": 10}}, 20),
+    # weak transmitters: nobody in range for most steps
+    "out_of_range": ([(0, 0), (199, 199)], 7, {"ue": {"velocity": 10}, "bs": {"tx": 5}}, 20),
+    # everyone on one BS
+    "single_bs": ([(100, 100)], 15, ep_cfg(25, {"ue": {"velocity": 7}, "bs": {"tx": 46}}), 25),
+    # distance ties: BSs mirrored around the map centre line, first-min tie-break matters
+    "tie_layout": ([(100, 60), (100, 140), (60, 100), (140, 100), (100, 60)], 15,
+                   ep_cfg(30, {"ue": {"velocity": 4}}), 30),
+}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name, (bs_xy, nue, cfg, steps) in CASES.items():
+        env = rh.make_fixed_layout_env(bs_xy, nue, config=cfg)
+        rec = rh.record_fork_episode(env, steps)
+        p = env.default_config()
+        from mobile_env.core.util import deep_dict_merge
+
+        p = deep_dict_merge(p, cfg)
+        rec["params"] = {
+            "width": p["width"], "height": p["height"],
+            "ep_time": min(p["EP_MAX_TIME"], p["arrival_params"]["ep_time"]),
+            "bw": p["bs"]["bw"], "freq": p["bs"]["freq"], "tx": p["bs"]["tx"], "bs_height": p["bs"]["height"],
+            "velocity": p["ue"]["velocity"], "snr_tr": p["ue"]["snr_tr"], "noise": p["ue"]["noise"],
+            "ue_height": p["ue"]["height"],
+            "util_lower": p["utility_params"]["lower"], "util_upper": p["utility_params"]["upper"],
+            "util_coeffs": list(p["utility_params"]["coeffs"]),
+        }
+        if name == "kat1":
+            s0 = rec["steps"][0]
+            assert [tuple(q) for q in s0["pos"]] == KAT1_POS, s0["pos"]
+            got = {(u, b): r for u, b, r in s0["pair_rates"]}
+            assert got == KAT1_RATES, got
+        if name == "kat2":
+            s19 = rec["steps"][19]
+            assert [tuple(q) for q in s19["pos"]] == KAT2_POS, s19["pos"]
+            got = {(u, b): r for u, b, r in s19["pair_rates"]}
+            assert got == KAT2_RATES, got
+        path = os.path.join(OUT, f"fork_{name}.json")
+        with open(path, "w") as f:
+            json.dump(rec, f, separators=(",", ":"))
+        print(name, "steps", steps, "bytes", os.path.getsize(path))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,198 @@
+"""TEST INFRASTRUCTURE ONLY -- drives the *real* reference from /root/reference.
+
+Nothing under ``oracle/`` is product code: only ``tests/``, ``__graft_entry__.smoke()``
+and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.
+
+This module exists so that the numpy restatement in ``oracle/mbe_oracle.py`` can be
+pinned against the reference's own ``MComCore.step`` (reference
+``mobile_env/core/base.py:230-296``) and so that golden vectors can be generated
+(``oracle/gen_golden.py`` -> ``tests/golden/*.json``).  It only works where
+``/root/reference`` exists (the build container); it never travels to the GPU box.
+
+The reference imports shapely / matplotlib / pygame / svgpath2mpl at module top
+(``core/base.py:8-15``, ``core/util.py:3-4,24-28``, ``core/entities.py:3``); none is
+installed here, so inert stand-ins are put into ``sys.modules`` first.  The only one
+with arithmetic is ``shapely.geometry.Point.distance`` (requirements.txt:9,
+shapely~=2.0.6): planar Euclidean distance of two points, restated with
+``math.hypot`` (call site ``core/channels.py:134``).
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("MBE_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "mobile_env", "core"))
+
+
+class _Point:
+    """Stand-in for shapely.geometry.Point (x, y, distance only)."""
+
+    def __init__(self, x, y):
+        self.x, self.y = x, y
+
+    def distance(self, other):
+        return math.hypot(self.x - other.x, self.y - other.y)
+
+
+class _Inert(types.ModuleType):
+    """Attribute-returning module used for the rendering libraries (never rendered)."""
+
+    def __getattr__(self, key):
+        if key.startswith("__"):
+            raise AttributeError(key)
+        return _Inert(self.__name__ + "." + key)
+
+    def __call__(self, *a, **k):
+        return _Inert("call")
+
+    def __isub__(self, other):
+        return self
+
+    def mean(self, *a, **k):
+        return 0
+
+
+def install_stubs() -> None:
+    if "shapely" not in sys.modules:
+        shp = types.ModuleType("shapely")
+        geo = types.ModuleType("shapely.geometry")
+        geo.Point = _Point
+        shp.geometry = geo
+        sys.modules["shapely"] = shp
+        sys.modules["shapely.geometry"] = geo
+    for name in (
+        "matplotlib",
+        "matplotlib.patheffects",
+        "matplotlib.pyplot",
+        "matplotlib.backends",
+        "matplotlib.backends.backend_agg",
+        "matplotlib.transforms",
+        "pygame",
+        "svgpath2mpl",
+    ):
+        if name not in sys.modules:
+            sys.modules[name] = _Inert(name)
+    if not hasattr(sys.modules["matplotlib"], "cm") or True:
+        sys.modules["matplotlib"].cm = _Inert("matplotlib.cm")
+
+
+def import_reference():
+    """Returns the reference's modules (base, entities, custom) -- unmodified code."""
+    if not reference_available():
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+    install_stubs()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    from mobile_env.core import base, entities  # noqa: E402
+    from mobile_env.scenarios import custom  # noqa: E402
+
+    return base, entities, custom
+
+
+def make_fixed_layout_env(bs_xy, num_ues, config=None, bs_params=None, ue_params=None):
+    """Reference env with a fixed BS list (what MComCustom does at custom.py:40-62,
+    minus the unseeded ``random`` BS generator) and JSON dumps disabled."""
+    base, entities, _ = import_reference()
+
+    class FixedLayoutEnv(base.MComCore):
+        def reset(self, *, seed=None):
+            super().reset(seed=seed)
+            users = [ue for ue in self.userDict.values() if ue.startTime <= 0]
+            self.activeUsers = sorted(users, key=lambda ue: ue.ue_id)
+            self.users_dataRateList = {ue.ue_id: [] for ue in self.userDict.values()}
+            self.users_trajectoryList = {ue.ue_id: [] for ue in self.userDict.values()}
+
+        def save_layout_and_data_rates(self, epoch_number, curr_step):  # dumps off
+            return
+
+    cfg = FixedLayoutEnv.default_config()
+    if config:
+        from mobile_env.core.util import deep_dict_merge
+
+        cfg = deep_dict_merge(cfg, config)
+    bsp = dict(cfg["bs"])
+    if bs_params:
+        bsp.update(bs_params)
+    uep = dict(cfg["ue"])
+    if ue_params:
+        uep.update(ue_params)
+    stations = [entities.BaseStation(i, tuple(xy), **bsp) for i, xy in enumerate(bs_xy)]
+    users = [entities.UserEquipment(i, **uep) for i in range(num_ues)]
+    return FixedLayoutEnv(stations, users, config or {})
+
+
+def record_fork_episode(env, steps, init_pos=None):
+    """Runs reset + ``steps`` reference steps, recording everything a parity test needs.
+
+    Returns a dict of plain lists: per step positions, the waypoint each UE held when it
+    moved (so the draw sequence can be injected), SNR matrix, connection index per UE,
+    per-(bs,ue) rounded rates, per-UE total rate, scaled utility, monitor scalars, done.
+    """
+    env.reset()
+    ues = [env.userDict[k] for k in sorted(env.userDict)]
+    bss = [env.stationDict[k] for k in sorted(env.stationDict)]
+    if init_pos is not None:
+        for ue, (x, y) in zip(ues, init_pos):
+            ue.x, ue.y = x, y
+    rec = {
+        "bs_xy": [[bs.x, bs.y] for bs in bss],
+        "init_pos": [[int(ue.x), int(ue.y)] for ue in ues],
+        "steps": [],
+    }
+    # wrap move() to log the waypoint each UE targets (movement.py:42-62)
+    mv = env.movementModel
+    orig_move = mv.move
+    targets = {}
+
+    def logged_move(ue):
+        had = ue in mv.userMoveDirection
+        out = orig_move(ue)
+        # waypoint used this call: either still stored, or equals the snap result
+        wp = mv.userMoveDirection.get(ue, out)
+        targets[ue.ue_id] = (int(wp[0]), int(wp[1]), 0 if had else 1)
+        return out
+
+    mv.move = logged_move
+    for s in range(steps):
+        targets.clear()
+        env.step(0, s)
+        # association used by this step's allocation (keys of bs2ue_dataRates, base.py:435);
+        # bs2ue_connections itself is emptied of leaving UEs at the last step (base.py:283-285)
+        conn = [-1] * len(ues)
+        for (bs, ue) in env.bs2ue_dataRates:
+            conn[ue.ue_id] = bs.bs_id
+        conn_after = [-1] * len(ues)
+        for bs, cues in env.bs2ue_connections.items():
+            for ue in cues:
+                conn_after[ue.ue_id] = bs.bs_id
+        snr = [[float(env.channelModel.calculateSNR(bs, ue)) for bs in bss] for ue in ues]
+        pair_rates = sorted(
+            [[ue.ue_id, bs.bs_id, float(r)] for (bs, ue), r in env.bs2ue_dataRates.items()]
+        )
+        info = env.monitor.info()
+        rec["steps"].append(
+            {
+                "pos": [[int(ue.x), int(ue.y)] for ue in ues],
+                "wp": [list(targets.get(ue.ue_id, (-1, -1, 0))) for ue in ues],
+                "snr": snr,
+                "conn": conn,
+                "conn_after": conn_after,
+                "pair_rates": pair_rates,
+                "rate": [float(env.allUserDataRates.get(ue, 0.0)) for ue in ues],
+                "utility": [float(env.ue_utilities.get(ue, float("nan"))) for ue in ues],
+                "n_connections": int(info["number connections"]),
+                "n_connected": int(info["number connected"]),
+                "mean_utility": float(info["mean utility"]),
+                "mean_datarate": float(info["mean datarate"]),
+                "time": float(env.time),
+                "done": bool(env.time_is_up),
+            }
+        )
+    mv.move = orig_move
+    return rec
