@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: env-steps/s of batched MComCore.step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one fused launch of the step kernel over one batch of ``--envs`` (default 65,536)
+mobile-medium-central environments per GPU (BASELINE.json configs[1]); envs shard over ranks
+with no collective (weak scaling: every GPU owns its own 65,536-env batches).  To keep the
+timed inputs out of L2 the bench rotates over R independent env batches whose combined
+footprint exceeds the 126 MB L2 (``config.l2``).  Steps are replayed from a CUDA graph.
+
+Printed JSON line (rank 0): value = whole-job env-steps/s with inputs resident in HBM;
+e2e = the same metric through the host-buffer C-ABI call (mbe_step_host: pinned host actions
+in, obs/reward/done out, copies inside the timed region); roofline = algorithmic bytes of the
+step kernel / its average duration against the measured HBM peak; cpu_baseline = the oracle's
+scalar port of the reference step timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (batched, whole box) for mobile-medium at 1/2/4/8 B200"
+UNIT = "env-steps/s"
+SIZES = {"mobile-small": (3, 5), "mobile-medium": (4, 15), "mobile-large": (13, 30)}
+
+
+def bytes_per_env_step(U: int, B: int, handler: str) -> dict:
+    """Algorithmic HBM bytes of one env-step for THIS build's layout and the
+    canonical int32/fp32 accounting of SURVEY.md section 8(d)."""
+    F = (2 * B + 1) if handler == "central" else (4 * B + 1)
+    mw = (B + 31) // 32
+    # pos r+w (int16x2) 8, waypoint read 4, actions 4, conn r+w 8*mw, rate f64 w 8, utility f32 w 4,
+    # obs f32 w 4F per UE; per env: reward, done, clock r+w, episode r, metrics
+    per_ue = 8 + 4 + 4 + 8 * mw + 8 + 4 + 4 * F
+    per_env = (4 if handler == "central" else 4 * U) + 1 + 8 + 4 + 16
+    ours = U * per_ue + per_env
+    canon = U * (32 + 8 * mw + 4 * F) + 13 if handler == "central" else U * (36 + 8 * mw + 4 * F) + 9
+    return {"layout": ours, "survey_8d": canon}
+
+
+class ClockSampler(threading.Thread):
+    """Polls NVML for SM clock and throttle reasons while the timed region runs."""
+
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTE = {"sw_power_cap": 0x4}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag, self.ok = [], set(), False, False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+
+    def sample(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in {**self.BAD, **self.NOTE}.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            self.sample()
+            time.sleep(0.002)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "samples": len(self.samples), "reasons": sorted(self.reasons)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per launch of the step kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get(workload)
+    return None
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle scalar port; the Python reference
+    itself cannot travel to the GPU box) on all host cores; each step is a bounded sample."""
+    if rank != 0:
+        return
+    from oracle import cpu_baseline
+
+    workload = args.workload
+    procs = os.cpu_count() or 1
+    total_steps = args.warmup + args.steps
+    seconds = max(0.5, min(5.0, 60.0 / max(total_steps, 1)))
+    vals = []
+    for i in range(total_steps):
+        r = cpu_baseline.run(workload, seconds, procs)
+        if i >= args.warmup:
+            vals.append(r)
+    value = statistics.mean(v["value"] for v in vals)
+    B, U = SIZES[workload.rsplit("-", 2)[0]]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "envs_per_gpu": args.envs, "bs": B, "ues": U,
+                   "note": "each step = every host core stepping its own env for a bounded time"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": vals[-1]["sample"], "single_core": vals[-1]["single_core"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mobile-medium-central-v0")
+    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU per batch")
+    ap.add_argument("--cpu-seconds", type=float, default=4.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    # CPU baseline first (rank 0, N=1 only), before CUDA is initialised in this process
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline
+
+        cpu = cpu_baseline.run(args.workload, args.cpu_seconds, os.cpu_count() or 1)
+
+    import torch
+    import torch.distributed as dist
+
+    import mobile_env_gan_b200 as mbe
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    size, handler = args.workload.rsplit("-", 2)[0], args.workload.split("-")[2]
+    B, U = SIZES[size]
+    E = args.envs
+    bpe = bytes_per_env_step(U, B, handler)
+    # rotate over R independent batches so that each step's inputs/outputs are not L2-resident
+    footprint = E * bpe["layout"]
+    R = max(2, -(-int(2.2 * 126e6) // footprint))
+    envs = []
+    for r in range(R):
+        env = mbe.make(args.workload, num_envs=E, device=str(dev), autoreset=True,
+                       env_offset=(rank * R + r) * E)
+        env.reset()
+        envs.append(env)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    for env in envs:  # synthetic policy output: uniform actions in [0, B]
+        env.actions.copy_(torch.randint(0, B + 1, (E, U), generator=g, device=dev, dtype=torch.int32))
+    stream = torch.cuda.Stream(device=dev)
+
+    def raw_steps(n, start=0):
+        for i in range(n):
+            envs[(start + i) % R].step(envs[(start + i) % R].actions)
+
+    chunk = R * 8
+    graph = None
+    with torch.cuda.stream(stream):
+        raw_steps(chunk)  # first touches outside the graph
+        torch.cuda.synchronize()
+        if not args.no_graph:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                raw_steps(chunk)
+
+        def run_steps(n):
+            done = 0
+            while graph is not None and n - done >= chunk:
+                graph.replay()
+                done += chunk
+            raw_steps(n - done)
+
+        # preheat (untimed) so that clocks are up, then W warm-up steps
+        t_end = time.perf_counter() + 0.3
+        while time.perf_counter() < t_end:
+            run_steps(chunk)
+            torch.cuda.synchronize()
+        run_steps(max(args.warmup, 3))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if sampler.ok:
+            sampler.sample()
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        run_steps(args.steps)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        sampler.stop_flag = True
+        sampler.join()
+        if sampler.ok:
+            sampler.sample()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        gpu_launches = args.steps  # one step_kernel launch per step (graph nodes included)
+
+        # ---- end to end through the host-buffer ABI call ----
+        e2e_steps = max(5, min(args.steps, 40))
+        F = envs[0].plan.feature_size
+        acts_h = [torch.randint(0, B + 1, (E, U), dtype=torch.int32).pin_memory() for _ in range(2)]
+        obs_h = torch.empty(E, U * F, dtype=torch.float32).pin_memory()
+        rew_h = torch.empty(E, dtype=torch.float32).pin_memory() if handler == "central" else \
+            torch.empty(E, U, dtype=torch.float32).pin_memory()
+        done_h = torch.empty(E, dtype=torch.uint8).pin_memory()
+        for i in range(3):
+            envs[i % R].step_host(acts_h[i % 2], obs_h, rew_h, done_h)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            envs[i % R].step_host(acts_h[i % 2], obs_h, rew_h, done_h)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        checksum = float(rew_h.sum())
+
+    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(times[0]), float(times[1])
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        per_launch_s = ms * 1e-3 / args.steps
+        achieved = bpe["layout"] * E / per_launch_s / 1e9
+        value = world * E * args.steps / (ms * 1e-3)
+        h2d = E * U * 4
+        d2h = E * U * F * 4 + rew_h.numel() * 4 + E
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": args.workload, "envs_per_gpu": E, "bs": B, "ues": U,
+                "actions": "uniform int32 in [0,B], resident in HBM", "autoreset": True, "ep_time": 20,
+                "l2": f"rotating {R} independent env batches, {R * footprint / 1e6:.0f} MB > 126 MB L2",
+                "launch": "CUDA graph replay" if graph is not None else "stream launches",
+            },
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "kernel": "mbe::step_kernel<1,0>",
+                "bytes_per_env_step": bpe["layout"], "bytes_per_env_step_survey_8d": bpe["survey_8d"],
+                "frac_survey_8d": bpe["survey_8d"] * E / per_launch_s / 1e9 / peak,
+            },
+            "cpu_baseline": cpu,
+            "e2e": {"value": world * E * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "mbe_step_host (pinned host buffers)",
+                    "checksum": checksum},
+            "gpu_launches": gpu_launches,
+            "clocks": sampler.result(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,175 @@
+/*
+ * mbe.h -- C ABI of libmbe.so: batched, GPU-resident replacement for the per-step hot path
+ * of mobile-env (reference fork yang-peilin/mobile-env-gan), i.e. MComCore.step over N
+ * independent environments (reference mobile_env/core/base.py:230-296).
+ *
+ * The reference is pure Python and has no FFI; the entry points below are what a binding
+ * for this path would need (INTEGRATION.md shows the ctypes stub a maintainer would add to
+ * mobile_env/core/base.py).  Each entry cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer inside mbe_buffers is a DEVICE pointer owned by the
+ *     caller (e.g. torch tensors) and must stay alive while bound;
+ *   - all calls are stream-ordered on the given cudaStream_t (passed as void*), enqueue
+ *     only, never synchronise (except the *_host convenience entry, which says so);
+ *   - return 0 on success, non-zero on error; mbe_last_error() gives a thread-local text;
+ *   - one handle per device; a handle is not thread-safe, different handles are.
+ *
+ * Data layout (structure of arrays, env-major; E = envs on this rank, U = UEs, B = BS slots,
+ * MW = ceil(B/32), F = 2B+1 (central) or 4B+1 (multi-agent)):
+ *   pos      int16 [E,U,2]   UE position (integers after the first move, movement.py:60)
+ *   wp       int16 [E,U,2]   current waypoint; x < 0 = none (movement.py:44-47,54-56)
+ *   t        int32 [E]       step clock of the episode (base.py:280, "time")
+ *   episode  int32 [E]       episode counter (-1 before the first reset)
+ *   bs_xy    int16 [B,2] or [E,B,2]  int-truncated BS coordinates (entities.py:24-26)
+ *   nbs      int32 [E]       live BS slots per env (random layouts, custom.py:68-77) or NULL
+ *   conn     uint32 [E,U,MW] GYM: connection bitmask (bs2ue_connections, base.py:76)
+ *   assoc    int32 [E,U]     FORK: BS index the UE is attached to, -1 = none (base.py:236-241)
+ *   actions  int32 [E,U]     GYM: 0 = NOOP (base.py:29), a>0 toggles BS a-1
+ *   rate     f64  [E,U]      per-UE total of the 2-decimal-rounded pair rates (base.py:413-435)
+ *   utility  f32  [E,U]      scaled utility in [-1,1] (utilities.py:44-55; base.py:253-258)
+ *   obs      f32  [E,U,F]    GYM observation written straight into the policy input
+ *   reward   f32  [E] (central) or [E,U] (multi-agent)
+ *   done     uint8 [E]       time_is_up (base.py:407-409)
+ *   metrics  f32  [E,4]      number connections, number connected, mean utility, mean
+ *                            datarate (metrics.py:5-28)
+ */
+#ifndef MBE_H_
+#define MBE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBE_ABI_VERSION 1
+
+enum { MBE_MODE_FORK = 0, MBE_MODE_GYM = 1 };
+enum { MBE_HANDLER_CENTRAL = 0, MBE_HANDLER_MA = 1 };
+enum { MBE_SCHED_RESOURCE_FAIR = 0 };
+enum { MBE_BS_SHARED = 0, MBE_BS_PER_ENV = 1 };
+enum { MBE_MAX_CLASSES = 8 };
+
+/* phases of one step (bit mask for mbe_stage); the fused step runs all of them in one launch.
+ * FORK order: MOVE, PRE, CLOCK.  GYM order: PRE, MOVE, CLOCK, POST. */
+enum {
+  MBE_PHASE_MOVE = 1,  /* RandomWaypointMovement.move         movement.py:42-62            */
+  MBE_PHASE_PRE = 2,   /* connectivity / association / action, scheduler split, utility,
+                          reward, metrics                     base.py:212-258, 421-435     */
+  MBE_PHASE_CLOCK = 4, /* time += 1, departures, done          base.py:280-291, 407-409     */
+  MBE_PHASE_POST = 8,  /* observation writer (GYM)                                          */
+  MBE_PHASE_ALL = 15
+};
+
+/* One class of base station (all BSs that share bw/freq/tx/height; UEs are homogeneous).
+ * The constants are folded on the host in FP64 from OkumuraHata.power_loss
+ * (channels.py:132-146) and Channel.calculateSNR (channels.py:24-27):
+ *    log2(snr(d2)) = l0 - k * log2(d2)   for d2 >= 1,   l_zero for d2 == 0 (EPSILON, channels.py:8)
+ * d2max is the largest integer squared distance with snr > snr_threshold (base.py:212-214)
+ * evaluated with the reference's own FP64 operation order; rate_lut[d2] (HOST pointer,
+ * d2max+1 doubles, copied by mbe_create) is Channel.datarate = bw*log2(1+snr) (channels.py:78-83). */
+typedef struct mbe_bs_class {
+  double l0;
+  double k;
+  double l_zero;
+  int32_t d2max; /* -1: never connectable */
+  int32_t reserved;
+  const double* rate_lut;
+} mbe_bs_class;
+
+typedef struct mbe_config {
+  int32_t abi_version; /* MBE_ABI_VERSION */
+  int32_t device;      /* CUDA device ordinal */
+  int32_t num_envs;    /* E on this rank */
+  int32_t num_ues;     /* U */
+  int32_t num_bs;      /* B (slots) */
+  int32_t mode;        /* MBE_MODE_* */
+  int32_t handler;     /* MBE_HANDLER_* (GYM) */
+  int32_t scheduler;   /* MBE_SCHED_* */
+  int32_t bs_layout;   /* MBE_BS_* */
+  int32_t bs_random_min, bs_random_max; /* >0: reset draws nbs in [min,max] and their
+                                           coordinates per env and episode (custom.py:68-77) */
+  int32_t autoreset;   /* GYM/FORK: re-initialise an env in the step that ends its episode */
+  int32_t reset_rng_episode; /* movement_params.reset_rng_episode (base.py:130-134) */
+  int32_t ep_time;     /* min(EP_MAX_TIME, max departure) (base.py:407-409) */
+  int32_t move_d2max;  /* largest integer d2 with sqrt(d2) <= velocity (movement.py:54) */
+  int64_t env_offset;  /* global id of local env 0 (multi-GPU sharding; Philox counters use it) */
+  uint64_t seed;       /* movement seed = config seed + 4 (base.py:155-170) */
+  double width, height;/* map (base.py:103) */
+  double velocity;     /* ue.velocity (base.py:119) */
+  double util_lower, util_upper, util_w1, util_w2, util_w3; /* utilities.py:30-55 */
+  int32_t num_classes; /* 1..MBE_MAX_CLASSES */
+  int32_t reserved;
+  mbe_bs_class classes[MBE_MAX_CLASSES];
+  const uint8_t* bs_class; /* HOST [B] class id per BS slot, or NULL = all class 0 */
+} mbe_config;
+
+typedef struct mbe_buffers {
+  int16_t* pos;
+  int16_t* wp;
+  int32_t* t;
+  int32_t* episode;
+  int16_t* bs_xy;
+  int32_t* nbs;          /* optional */
+  uint32_t* conn;        /* GYM */
+  int32_t* assoc;        /* FORK */
+  const int32_t* actions;/* GYM */
+  double* rate;          /* optional in GYM */
+  float* utility;        /* required (carried between phases) */
+  float* obs;            /* GYM */
+  float* reward;         /* GYM */
+  uint8_t* done;
+  float* metrics;        /* optional */
+  float* dbg_snr;        /* optional f32 [E,U,B]: SNR at the positions the PRE phase sees */
+  /* replay of reference trajectories: waypoints injected instead of Philox draws */
+  const int16_t* inj_wp; /* optional int16 [E,U,K,2] */
+  int32_t* wp_cnt;       /* int32 [E,U] draws consumed so far (required with inj_wp) */
+  int32_t inj_k;         /* K */
+  int32_t reserved;
+} mbe_buffers;
+
+typedef struct mbe_env mbe_env;
+
+/* library / build information */
+int mbe_abi_version(void);
+const char* mbe_build_info(void);
+const char* mbe_last_error(void);
+
+/* replaces MComCore.__init__ (base.py:32-100): validates, copies the constant tables */
+int mbe_create(const mbe_config* cfg, mbe_env** out);
+void mbe_destroy(mbe_env* env);
+
+/* binds caller-owned device buffers (the SoA state of entities.py:6-57 / base.py:69-79) */
+int mbe_bind(mbe_env* env, const mbe_buffers* bufs);
+
+/* replaces MComCore.reset + MComCustom.reset (base.py:172-209, custom.py:40-62) for the envs
+ * whose mask byte is non-zero (DEVICE pointer, NULL = all): clock, initial positions
+ * (movement.py:64-72), optional BS layout, cleared connections, reset observation. */
+int mbe_reset(mbe_env* env, const uint8_t* env_mask, void* stream);
+
+/* replaces MComCore.step (base.py:230-296): one fused launch over all bound envs */
+int mbe_step(mbe_env* env, void* stream);
+
+/* the same step split into phases (MBE_PHASE_* mask), for per-stage parity and profiling */
+int mbe_stage(mbe_env* env, int phase_mask, void* stream);
+
+/* Channel.calculateSNR for every UE x BS pair (channels.py:24-27): f32 [E,U,B] into out_snr,
+ * connectable bitmask uint32 [E,U,MW] into out_elig (either may be NULL) */
+int mbe_channel(mbe_env* env, float* out_snr, uint32_t* out_elig, void* stream);
+
+/* recompute the observation of the current state (after the caller edited pos / conn) */
+int mbe_observe(mbe_env* env, void* stream);
+
+/* number of kernel launches this handle has enqueued so far */
+int64_t mbe_launch_count(const mbe_env* env);
+
+/* Host-buffer convenience: H2D actions, step, D2H obs/reward/done, then synchronises the
+ * stream.  Host pointers should be pinned.  NULL pointers are skipped. */
+int mbe_step_host(mbe_env* env, const int32_t* actions_host, float* obs_host,
+                  float* reward_host, uint8_t* done_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBE_H_ */

@@ -1,0 +1,445 @@
+"""Batched, GPU-resident ``MComCore``.
+
+Same constructor, config dictionary, plugin keys and attribute names as the reference
+(mobile_env/core/base.py:28-296), but one object holds ``num_envs`` independent environments
+as structure-of-arrays tensors on one B200 and ``step`` is a single fused CUDA launch through
+the C ABI of ``libmbe.so`` (include/mbe.h).  There is no CPU fallback.
+
+Two step semantics behind one kernel set:
+
+``mode="fork"``  the reference's real step: move -> nearest connectable BS -> ResourceFair split
+                 -> utility (base.py:230-296).  ``step(epoch_number, curr_step)`` returns None
+                 and results are read from attributes, like the reference.
+``mode="gym"``   Gymnasium-shaped: ``step(actions) -> obs, reward, terminated, truncated, info``
+                 with the central / multi-agent handlers (the fork dropped them; semantics are
+                 this build's specification, see oracle/mbe_oracle.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from . import metrics as _metrics
+from .arrival import Arrival, NoDeparture
+from .channels import Channel, OkumuraHata
+from .entities import BaseStation, UserEquipment
+from .logging import Monitor
+from .movement import Movement, RandomWaypointMovement
+from .schedules import ResourceFair, Scheduler
+from .util import deep_dict_merge
+from .utilities import BoundedLogUtility, Utility
+
+MAX_COORD = 32767
+
+
+@dataclass
+class Plan:
+    """Everything the C ABI needs, folded on the host (no GPU required to build it)."""
+
+    num_envs: int
+    num_ues: int
+    num_bs: int
+    mode: int
+    handler: int
+    bs_layout: int
+    bs_random: tuple
+    autoreset: bool
+    reset_rng_episode: bool
+    ep_time: int
+    env_offset: int
+    seed: int
+    width: float
+    height: float
+    velocity: float
+    move_d2max: int
+    utility: tuple
+    classes: List[dict] = field(default_factory=list)
+    bs_class: Optional[np.ndarray] = None
+    bs_xy: Optional[np.ndarray] = None  # shared layout [B,2] int16
+
+    @property
+    def feature_size(self) -> int:
+        if self.mode != _lib.MODE_GYM:
+            return 0
+        return (4 if self.handler == _lib.HANDLER_MA else 2) * self.num_bs + 1
+
+
+class MComCore:
+    NOOP_ACTION = 0
+    metadata = {"render_modes": ["rgb_array", "human"]}
+
+    # ------------------------------------------------------------------ configuration --
+    @classmethod
+    def default_config(cls) -> Dict:
+        """Reference defaults (base.py:102-153) plus the batching keys of this build."""
+        width, height, ep_time = 200, 200, 20
+        return {
+            "width": width,
+            "height": height,
+            "EP_MAX_TIME": ep_time,
+            "seed": 2024,
+            "reset_rng_episode": False,
+            "arrival": NoDeparture,
+            "channel": OkumuraHata,
+            "scheduler": ResourceFair,
+            "movement": RandomWaypointMovement,
+            "utility": BoundedLogUtility,
+            "bs": {"bw": 9e6, "freq": 2500, "tx": 40, "height": 50},
+            "ue": {"velocity": 1.5, "snr_tr": 2e-8, "noise": 1e-9, "height": 1.6},
+            "arrival_params": {"ep_time": ep_time, "reset_rng_episode": False},
+            "channel_params": {},
+            "scheduler_params": {},
+            "movement_params": {"width": width, "height": height, "reset_rng_episode": True},
+            "utility_params": {"lower": -20, "upper": 20, "coeffs": (10, 0, 10)},
+            "metrics": {"scalar_metrics": {}, "ue_metrics": {}, "bs_metrics": {}},
+            # ---- batching (new) ----
+            "num_envs": 1,
+            "env_offset": 0,  # global id of local env 0 when envs are sharded over GPUs
+            "device": "cuda",
+            "mode": "fork",  # "fork" | "gym"
+            "handler": "central",  # "central" | "ma" (gym mode)
+            "autoreset": False,
+            "bs_random": None,  # (min, max): draw a BS layout per env and episode (custom.py:68-77)
+            "max_bs": None,  # BS slots when bs_random is used
+        }
+
+    @classmethod
+    def seeding(cls, config: Dict) -> Dict:
+        """Per-plugin seeds seed+1..seed+5 (base.py:155-170); movement gets seed+4."""
+        for num, key in enumerate(
+            ("arrival_params", "channel_params", "scheduler_params", "movement_params", "utility_params")
+        ):
+            config.setdefault(key, {})["seed"] = config["seed"] + num + 1
+        return config
+
+    # ------------------------------------------------------------------------- planning --
+    @classmethod
+    def build_plan(cls, stations: List[BaseStation], users: List[UserEquipment], config: Dict, plugins=None) -> Plan:
+        """Maps plugin objects and entity parameters to the device description. Pure host code."""
+        if plugins is None:
+            plugins = cls._instantiate_plugins(config)
+        arrival, channel, scheduler, movement, utility = plugins
+        if not isinstance(arrival, NoDeparture):
+            raise NotImplementedError(f"arrival {type(arrival).__name__}: only NoDeparture has a CUDA kernel")
+        if not isinstance(scheduler, ResourceFair):
+            raise NotImplementedError(f"scheduler {type(scheduler).__name__}: only ResourceFair has a CUDA kernel")
+        if not isinstance(utility, BoundedLogUtility):
+            raise NotImplementedError(f"utility {type(utility).__name__}: only BoundedLogUtility has a CUDA kernel")
+        if not isinstance(channel, Channel):
+            raise TypeError("channel must derive from Channel")
+        if not users:
+            raise ValueError("at least one UE is required")
+        ue0 = users[0]
+        if any(ue.radio_key() != ue0.radio_key() for ue in users):
+            raise NotImplementedError("heterogeneous UE parameters are not supported by the kernels")
+        width, height = float(config["width"]), float(config["height"])
+        if not (0 < width <= MAX_COORD and 0 < height <= MAX_COORD):
+            raise ValueError("map does not fit int16 coordinates")
+        mode = {"fork": _lib.MODE_FORK, "gym": _lib.MODE_GYM}[config["mode"]]
+        handler = {"central": _lib.HANDLER_CENTRAL, "ma": _lib.HANDLER_MA}[config.get("handler") or "central"]
+        bs_random = config.get("bs_random")
+        max_d2 = int(width) ** 2 + int(height) ** 2 + 2
+        if bs_random:
+            nbs = int(config.get("max_bs") or bs_random[1])
+            proto = BaseStation(0, (0, 0), **config["bs"])
+            classes = [channel.fold(proto, ue0, max_d2)]
+            bs_class, bs_xy, layout = None, None, _lib.BS_PER_ENV
+            bs_random = (int(bs_random[0]), int(bs_random[1]))
+        else:
+            if not stations:
+                raise ValueError("stations are required unless config['bs_random'] is set")
+            stations = sorted(stations, key=lambda b: b.bs_id)
+            nbs = len(stations)
+            keys, classes = [], []
+            bs_class = np.zeros(nbs, dtype=np.uint8)
+            for i, bs in enumerate(stations):
+                k = bs.radio_key()
+                if k not in keys:
+                    keys.append(k)
+                    classes.append(channel.fold(bs, ue0, max_d2))
+                bs_class[i] = keys.index(k)
+            if len(classes) > _lib.MAX_CLASSES:
+                raise NotImplementedError(f"more than {_lib.MAX_CLASSES} distinct BS parameter sets")
+            bs_xy = np.array([[int(b.x), int(b.y)] for b in stations], dtype=np.int16)  # entities.py:24-26
+            layout, bs_random = _lib.BS_SHARED, (0, 0)
+        mv = movement.device_params(ue0.velocity)
+        w1, w2, w3 = utility.coeffs
+        ep_time = int(min(config["EP_MAX_TIME"], arrival.ep_time))  # base.py:407-409 with NoDeparture
+        return Plan(
+            num_envs=int(config["num_envs"]), num_ues=len(users), num_bs=nbs, mode=mode, handler=handler,
+            bs_layout=layout, bs_random=bs_random, autoreset=bool(config.get("autoreset")),
+            reset_rng_episode=bool(movement.reset_rng_episode), ep_time=ep_time,
+            env_offset=int(config.get("env_offset", 0)), seed=int(movement.seed),
+            width=width, height=height, velocity=mv["velocity"], move_d2max=mv["move_d2max"],
+            utility=(float(utility.lower), float(utility.upper), float(w1), float(w2), float(w3)),
+            classes=classes, bs_class=bs_class, bs_xy=bs_xy,
+        )
+
+    @staticmethod
+    def _instantiate_plugins(config):
+        return (
+            config["arrival"](**config["arrival_params"]),
+            config["channel"](**config["channel_params"]),
+            config["scheduler"](**config["scheduler_params"]),
+            config["movement"](**config["movement_params"]),
+            config["utility"](**config["utility_params"]),
+        )
+
+    # ---------------------------------------------------------------------- construction --
+    def __init__(self, stations: List[BaseStation], users: List[UserEquipment], config=None, render_mode=None):
+        assert render_mode in self.metadata["render_modes"] + [None]
+        self.render_mode = render_mode  # rendering is out of scope (base.py:466-753)
+        config = deep_dict_merge(self.default_config(), config or {})
+        config = self.seeding(config)
+        self.config = config
+        self.width, self.height = config["width"], config["height"]
+        self.seed = config["seed"]
+        self.reset_rng_episode = config["reset_rng_episode"]
+        self.EP_MAX_TIME = config["EP_MAX_TIME"]
+        plugins = self._instantiate_plugins(config)
+        (self.arrivalModel, self.channelModel, self.schedulerModel, self.movementModel, self.utilityModel) = plugins
+        # upstream spellings
+        self.arrival, self.channel, self.scheduler, self.movement, self.utility = plugins
+        self.stationDict = {bs.bs_id: bs for bs in stations}
+        self.userDict = {ue.ue_id: ue for ue in users}
+        self.stations, self.users = self.stationDict, self.userDict
+        self.NUM_USERS = len(self.userDict)
+        self.closed = False
+
+        self.plan = self.build_plan(list(stations), list(users), config, plugins)
+        self.NUM_STATIONS = self.plan.num_bs
+        self.num_envs = self.plan.num_envs
+        self.mode = config["mode"]
+
+        config["metrics"]["scalar_metrics"].update(
+            {
+                "number connections": _metrics.number_connections,
+                "number connected": _metrics.number_connected,
+                "mean utility": _metrics.mean_utility,
+                "mean datarate": _metrics.mean_datarate,
+            }
+        )
+        self.monitor = Monitor(**config["metrics"])
+
+        self._lib = _lib.load()  # raises if libmbe.so is not built: no CPU fallback
+        if not torch.cuda.is_available():
+            raise _lib.MbeError("MComCore needs a CUDA device (B200); there is no CPU fallback for step()")
+        self.device = torch.device(config["device"])
+        if self.device.type != "cuda":
+            raise _lib.MbeError("config['device'] must be a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._handle = C.c_void_p()
+        self._keepalive = []
+        self._create_handle()
+        self._allocate()
+        self._bind()
+        self._needs_reset = True
+
+    def _create_handle(self):
+        p = self.plan
+        cfg = _lib.Config()
+        cfg.abi_version = _lib.MBE_ABI_VERSION
+        cfg.device = self.device.index
+        cfg.num_envs, cfg.num_ues, cfg.num_bs = p.num_envs, p.num_ues, p.num_bs
+        cfg.mode, cfg.handler, cfg.scheduler = p.mode, p.handler, _lib.SCHED_RESOURCE_FAIR
+        cfg.bs_layout = p.bs_layout
+        cfg.bs_random_min, cfg.bs_random_max = p.bs_random
+        cfg.autoreset = int(p.autoreset)
+        cfg.reset_rng_episode = int(p.reset_rng_episode)
+        cfg.ep_time = p.ep_time
+        cfg.move_d2max = p.move_d2max
+        cfg.env_offset = p.env_offset
+        cfg.seed = p.seed & 0xFFFFFFFFFFFFFFFF
+        cfg.width, cfg.height, cfg.velocity = p.width, p.height, p.velocity
+        cfg.util_lower, cfg.util_upper, cfg.util_w1, cfg.util_w2, cfg.util_w3 = p.utility
+        cfg.num_classes = len(p.classes)
+        for i, c in enumerate(p.classes):
+            lut = np.ascontiguousarray(c["rate_lut"], dtype=np.float64)
+            self._keepalive.append(lut)
+            cfg.classes[i].l0, cfg.classes[i].k, cfg.classes[i].l_zero = c["l0"], c["k"], c["l_zero"]
+            cfg.classes[i].d2max = c["d2max"]
+            cfg.classes[i].rate_lut = lut.ctypes.data_as(C.POINTER(C.c_double)) if len(lut) else None
+        if p.bs_class is not None:
+            self._keepalive.append(p.bs_class)
+            cfg.bs_class = p.bs_class.ctypes.data_as(C.POINTER(C.c_uint8))
+        _lib.check(self._lib.mbe_create(C.byref(cfg), C.byref(self._handle)))
+
+    def _allocate(self):
+        p, dev = self.plan, self.device
+        E, U, B = p.num_envs, p.num_ues, p.num_bs
+        z = lambda *s, dt: torch.zeros(*s, dtype=dt, device=dev)  # noqa: E731
+        self.pos = z(E, U, 2, dt=torch.int16)
+        self.wp = torch.full((E, U, 2), -1, dtype=torch.int16, device=dev)
+        self.t = z(E, dt=torch.int32)
+        self.episode = torch.full((E,), -1, dtype=torch.int32, device=dev)
+        if p.bs_layout == _lib.BS_SHARED:
+            self.bs_xy = torch.from_numpy(p.bs_xy).to(dev)
+            self.nbs = None
+        else:
+            self.bs_xy = z(E, B, 2, dt=torch.int16)
+            self.nbs = torch.full((E,), B, dtype=torch.int32, device=dev)
+        self.rate = z(E, U, dt=torch.float64)
+        self.utility_scaled = torch.full((E, U), -1.0, dtype=torch.float32, device=dev)
+        self.done = z(E, dt=torch.uint8)
+        self._terminated = z(E, dt=torch.bool)  # no natural termination, only truncation
+        self.metrics = z(E, 4, dt=torch.float32)
+        gym = p.mode == _lib.MODE_GYM
+        self.conn = z(E, U, dt=torch.int32) if gym else None
+        self.actions = z(E, U, dt=torch.int32) if gym else None
+        self.obs = z(E, U, p.feature_size, dt=torch.float32) if gym else None
+        self.reward = (z(E, U, dt=torch.float32) if p.handler == _lib.HANDLER_MA else z(E, dt=torch.float32)) if gym else None
+        self.assoc = None if gym else torch.full((E, U), -1, dtype=torch.int32, device=dev)
+        self.dbg_snr = None
+        self.inj_wp = None
+        self.wp_cnt = None
+
+    def _bind(self):
+        ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        b = _lib.Buffers()
+        b.pos, b.wp, b.t, b.episode, b.bs_xy, b.nbs = map(ptr, (self.pos, self.wp, self.t, self.episode, self.bs_xy, self.nbs))
+        b.conn, b.assoc, b.actions = ptr(self.conn), ptr(self.assoc), ptr(self.actions)
+        b.rate, b.utility, b.obs, b.reward = ptr(self.rate), ptr(self.utility_scaled), ptr(self.obs), ptr(self.reward)
+        b.done, b.metrics, b.dbg_snr = ptr(self.done), ptr(self.metrics), ptr(self.dbg_snr)
+        b.inj_wp, b.wp_cnt = ptr(self.inj_wp), ptr(self.wp_cnt)
+        b.inj_k = 0 if self.inj_wp is None else self.inj_wp.shape[2]
+        _lib.check(self._lib.mbe_bind(self._handle, C.byref(b)))
+
+    # ------------------------------------------------------------------------ test hooks --
+    def enable_debug_snr(self):
+        """Allocates the optional [E,U,B] SNR output of the PRE phase."""
+        p = self.plan
+        self.dbg_snr = torch.zeros(p.num_envs, p.num_ues, p.num_bs, dtype=torch.float32, device=self.device)
+        self._bind()
+        return self.dbg_snr
+
+    def inject_waypoints(self, waypoints):
+        """Replays reference trajectories: ``waypoints`` int [E,U,K,2] are consumed in order per UE
+        instead of Philox draws (movement.py:44-47)."""
+        wp = torch.as_tensor(waypoints).to(device=self.device, dtype=torch.int16).contiguous()
+        assert wp.dim() == 4 and wp.shape[:2] == self.pos.shape[:2] and wp.shape[3] == 2
+        self.inj_wp = wp
+        self.wp_cnt = torch.zeros(wp.shape[:2], dtype=torch.int32, device=self.device)
+        self._bind()
+
+    def set_positions(self, pos):
+        self.pos.copy_(torch.as_tensor(pos).to(device=self.device, dtype=torch.int16))
+
+    def set_station_positions(self, bs_xy, nbs=None):
+        self.bs_xy.copy_(torch.as_tensor(bs_xy).to(device=self.device, dtype=torch.int16))
+        if nbs is not None:
+            self.nbs.copy_(torch.as_tensor(nbs).to(device=self.device, dtype=torch.int32))
+
+    # ----------------------------------------------------------------------------- run ----
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self, *, seed=None, options=None, env_mask=None):
+        """MComCore.reset (base.py:172-209) for all envs, or those selected by ``env_mask``
+        (uint8/bool tensor [E]).  GYM mode returns ``(obs, info)``."""
+        if seed is not None:
+            self.seed = seed  # like the reference: stored, plugins keep their seeds (base.py:178-180)
+        for m in (self.arrivalModel, self.channelModel, self.schedulerModel, self.movementModel, self.utilityModel):
+            m.reset()
+        mask_ptr = None
+        if env_mask is not None:
+            env_mask = env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            mask_ptr = C.c_void_p(env_mask.data_ptr())
+        _lib.check(self._lib.mbe_reset(self._handle, mask_ptr, self._stream()))
+        self.monitor.reset()
+        self._needs_reset = False
+        if self.plan.mode == _lib.MODE_GYM:
+            return self._obs_view(), {}
+        return None
+
+    def _obs_view(self):
+        if self.plan.handler == _lib.HANDLER_CENTRAL:
+            return self.obs.view(self.num_envs, -1)
+        return self.obs
+
+    def step(self, *args):
+        """FORK: ``step(epoch_number, curr_step)`` -> None (base.py:230-296).
+        GYM: ``step(actions)`` -> ``obs, reward, terminated, truncated, info``."""
+        if self._needs_reset:
+            raise RuntimeError("call reset() before step()")
+        if self.plan.mode == _lib.MODE_FORK:
+            _lib.check(self._lib.mbe_step(self._handle, self._stream()))
+            return None
+        (actions,) = args
+        if actions is not self.actions:
+            self.actions.copy_(torch.as_tensor(actions).reshape(self.actions.shape), non_blocking=True)
+        _lib.check(self._lib.mbe_step(self._handle, self._stream()))
+        # views only: no extra kernels on the step path (truncated aliases the done bytes)
+        return self._obs_view(), self.reward, self._terminated, self.done.view(torch.bool), {"metrics": self.metrics}
+
+    def stage(self, phase_mask: int):
+        _lib.check(self._lib.mbe_stage(self._handle, int(phase_mask), self._stream()))
+
+    def observe(self):
+        _lib.check(self._lib.mbe_observe(self._handle, self._stream()))
+        return self._obs_view()
+
+    def channel_snr(self, want_elig=False):
+        """Channel.calculateSNR for every UE x BS pair (channels.py:24-27) -> f32 [E,U,B]."""
+        p = self.plan
+        snr = torch.empty(p.num_envs, p.num_ues, p.num_bs, dtype=torch.float32, device=self.device)
+        elig = torch.empty(p.num_envs, p.num_ues, dtype=torch.int32, device=self.device) if want_elig else None
+        _lib.check(
+            self._lib.mbe_channel(self._handle, C.c_void_p(snr.data_ptr()),
+                                  None if elig is None else C.c_void_p(elig.data_ptr()), self._stream())
+        )
+        return (snr, elig) if want_elig else snr
+
+    def step_host(self, actions_host, obs_host, reward_host, done_host):
+        """Host-buffer step through ``mbe_step_host`` (pinned numpy/torch CPU tensors)."""
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        _lib.check(self._lib.mbe_step_host(self._handle, ptr(actions_host), ptr(obs_host), ptr(reward_host),
+                                           ptr(done_host), self._stream()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.mbe_launch_count(self._handle))
+
+    @property
+    def time_is_up(self):
+        """base.py:407-409, per env."""
+        return self.done.view(torch.bool)
+
+    @property
+    def time(self):
+        return self.t
+
+    # ------------------------------------------------------------- reference-named views --
+    def view(self, e: int = 0):
+        """Host-side snapshot of env ``e`` with the reference's attribute names
+        (stationDict, userDict, activeUsers, bs2ue_connections, bs2ue_dataRates,
+        allUserDataRates, ue_utilities, time).  Slow path: synchronises and copies."""
+        from .views import EnvView
+
+        return EnvView(self, e)
+
+    def state_dict(self):
+        keys = ("pos", "wp", "t", "episode", "bs_xy", "nbs", "conn", "assoc", "rate", "utility_scaled", "done")
+        return {k: getattr(self, k).clone() for k in keys if getattr(self, k) is not None}
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            getattr(self, k).copy_(v)
+        self._needs_reset = False
+
+    def close(self):
+        if getattr(self, "_handle", None) and self._handle.value:
+            self._lib.mbe_destroy(self._handle)
+            self._handle = C.c_void_p()
+        self.closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

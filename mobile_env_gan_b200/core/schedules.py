@@ -1,0 +1,35 @@
+"""Scheduler plugins (reference mobile_env/core/schedules.py)."""
+from __future__ import annotations
+
+from typing import List
+
+
+class Scheduler:
+    kernel_id = None
+
+    def __init__(self, **kwargs):
+        pass
+
+    def reset(self) -> None:
+        pass
+
+    def share(self, bs, rates: List[float]) -> List[float]:
+        raise NotImplementedError
+
+
+class ResourceFair(Scheduler):
+    """Equal split of the BS's resources: rate / n (schedules.py:20-22)."""
+
+    kernel_id = 0
+
+    def share(self, bs, rates):
+        n = len(rates)
+        return [r / n for r in rates]
+
+
+class RateFair(Scheduler):
+    """Listed for completeness: the reference's RateFair.share returns a scalar
+    (schedules.py:26-29) and cannot be used by allocateDataRate2User (base.py:435)."""
+
+    def share(self, bs, rates):
+        raise NotImplementedError("RateFair is broken in the reference (returns a scalar); not built")

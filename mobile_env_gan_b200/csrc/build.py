@@ -1,0 +1,48 @@
+"""Builds libmbe.so in-tree with nvcc for sm_100a (the only target)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libmbe.so")
+SOURCES = ["mbe.cu"]
+DEPS = ["mbe.cu", "mbe_step.cuh", "mbe_device.cuh", os.path.join("..", "..", "include", "mbe.h")]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(HERE, d)) > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return LIB
+    cmd = [
+        nvcc_path(), "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+        "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+        "--expt-relaxed-constexpr", "--extended-lambda",
+        "-Xptxas", "-v" if verbose else "-O3",
+        "-o", LIB,
+    ] + [os.path.join(HERE, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

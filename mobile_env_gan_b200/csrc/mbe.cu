@@ -1,0 +1,299 @@
+// libmbe.so -- C ABI (include/mbe.h) over the sm_100a kernels in mbe_step.cuh.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mbe.h"
+#include "mbe_step.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define MBE_CUDA(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t e_ = (expr);                                                               \
+    if (e_ != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(e_));    \
+  } while (0)
+
+}  // namespace
+
+struct mbe_env {
+  mbe_config cfg;
+  mbe_buffers bufs;
+  bool bound = false;
+  mbe::StepArgs args;
+  std::vector<double*> luts;
+  uint8_t* d_bs_class = nullptr;
+  size_t smem = 0;
+  int grid = 0;
+  int64_t launches = 0;
+};
+
+extern "C" {
+
+int mbe_abi_version(void) { return MBE_ABI_VERSION; }
+
+const char* mbe_build_info(void) {
+  return "libmbe abi " "1" " | sm_100a | built " __DATE__ " " __TIME__;
+}
+
+const char* mbe_last_error(void) { return g_err.c_str(); }
+
+int mbe_create(const mbe_config* cfg, mbe_env** out) {
+  if (!cfg || !out) return fail("mbe_create: null argument");
+  *out = nullptr;
+  if (cfg->abi_version != MBE_ABI_VERSION)
+    return fail("mbe_create: abi_version %d, library is %d", cfg->abi_version, MBE_ABI_VERSION);
+  if (cfg->num_envs <= 0) return fail("mbe_create: num_envs must be > 0");
+  if (cfg->num_ues <= 0 || cfg->num_ues > 32)
+    return fail("mbe_create: num_ues=%d not supported by the warp-segment kernel (1..32)", cfg->num_ues);
+  if (cfg->num_bs <= 0 || cfg->num_bs > 32)
+    return fail("mbe_create: num_bs=%d not supported by the warp-segment kernel (1..32)", cfg->num_bs);
+  if (cfg->mode != MBE_MODE_FORK && cfg->mode != MBE_MODE_GYM) return fail("mbe_create: bad mode %d", cfg->mode);
+  if (cfg->handler != MBE_HANDLER_CENTRAL && cfg->handler != MBE_HANDLER_MA)
+    return fail("mbe_create: bad handler %d", cfg->handler);
+  if (cfg->scheduler != MBE_SCHED_RESOURCE_FAIR) return fail("mbe_create: scheduler %d not available", cfg->scheduler);
+  if (cfg->num_classes < 1 || cfg->num_classes > MBE_MAX_CLASSES)
+    return fail("mbe_create: num_classes=%d out of range", cfg->num_classes);
+  if (!(cfg->width > 0 && cfg->width <= 32767 && cfg->height > 0 && cfg->height <= 32767))
+    return fail("mbe_create: map %gx%g does not fit int16 coordinates", cfg->width, cfg->height);
+  if (cfg->ep_time <= 0) return fail("mbe_create: ep_time must be > 0");
+  if (cfg->bs_random_max > 0 &&
+      (cfg->bs_layout != MBE_BS_PER_ENV || cfg->bs_random_min < 1 || cfg->bs_random_max > cfg->num_bs ||
+       cfg->bs_random_min > cfg->bs_random_max))
+    return fail("mbe_create: random BS layouts need bs_layout=PER_ENV and 1 <= min <= max <= num_bs");
+  if (!(cfg->util_upper > cfg->util_lower) || !(cfg->util_w3 > 0) || cfg->util_w3 == 1.0)
+    return fail("mbe_create: bad utility parameters");
+  for (int c = 0; c < cfg->num_classes; ++c)
+    if (cfg->classes[c].d2max >= 0 && !cfg->classes[c].rate_lut)
+      return fail("mbe_create: class %d has no rate_lut", c);
+
+  MBE_CUDA(cudaSetDevice(cfg->device));
+  mbe_env* env = new (std::nothrow) mbe_env();
+  if (!env) return fail("mbe_create: out of host memory");
+  env->cfg = *cfg;
+  std::memset(&env->bufs, 0, sizeof env->bufs);
+  mbe::StepArgs& a = env->args;
+  std::memset(&a, 0, sizeof a);
+  a.E = cfg->num_envs;
+  a.U = cfg->num_ues;
+  a.B = cfg->num_bs;
+  const bool gym = cfg->mode == MBE_MODE_GYM, ma = cfg->handler == MBE_HANDLER_MA;
+  a.F = gym ? (ma ? 4 * a.B + 1 : 2 * a.B + 1) : 0;
+  a.epw = 32 / a.U;
+  a.epb = a.epw * mbe::kWarpsPerBlock;
+  a.env_offset = (unsigned)cfg->env_offset;
+  a.ep_time = cfg->ep_time;
+  a.autoreset = cfg->autoreset;
+  a.reset_rng_episode = cfg->reset_rng_episode;
+  a.bs_per_env = cfg->bs_layout == MBE_BS_PER_ENV;
+  a.bs_rand_min = cfg->bs_random_min;
+  a.bs_rand_max = cfg->bs_random_max;
+  a.seed_lo = (unsigned)(cfg->seed & 0xffffffffu);
+  a.seed_hi = (unsigned)(cfg->seed >> 32);
+  a.width = cfg->width;
+  a.height = cfg->height;
+  a.velocity = cfg->velocity;
+  a.move_d2max = cfg->move_d2max;
+  a.util_c = (float)(cfg->util_w1 * std::log(2.0) / std::log(cfg->util_w3));
+  a.util_w2 = (float)cfg->util_w2;
+  a.util_lo = (float)cfg->util_lower;
+  a.util_hi = (float)cfg->util_upper;
+  a.util_scale = (float)(2.0 / (cfg->util_upper - cfg->util_lower));
+  a.n_classes = cfg->num_classes;
+  for (int c = 0; c < cfg->num_classes; ++c) {
+    const mbe_bs_class& h = cfg->classes[c];
+    mbe::ClassDev& d = a.cls[c];
+    d.l0_hi = (float)h.l0;
+    d.l0_lo = (float)(h.l0 - (double)d.l0_hi);
+    d.k_hi = (float)h.k;
+    d.k_lo = (float)(h.k - (double)d.k_hi);
+    d.l_zero = (float)h.l_zero;
+    d.d2max = h.d2max;
+    d.lut = nullptr;
+    if (h.d2max >= 0) {
+      double* p = nullptr;
+      size_t bytes = ((size_t)h.d2max + 1) * sizeof(double);
+      cudaError_t e = cudaMalloc(&p, bytes);
+      if (e == cudaSuccess) e = cudaMemcpy(p, h.rate_lut, bytes, cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) {
+        mbe_destroy(env);
+        return fail("mbe_create: rate_lut upload failed: %s", cudaGetErrorString(e));
+      }
+      env->luts.push_back(p);
+      d.lut = p;
+    }
+  }
+  if (cfg->bs_class) {
+    for (int b = 0; b < cfg->num_bs; ++b)
+      if (cfg->bs_class[b] >= cfg->num_classes) {
+        mbe_destroy(env);
+        return fail("mbe_create: bs_class[%d]=%d >= num_classes", b, cfg->bs_class[b]);
+      }
+    cudaError_t e = cudaMalloc(&env->d_bs_class, cfg->num_bs);
+    if (e == cudaSuccess) e = cudaMemcpy(env->d_bs_class, cfg->bs_class, cfg->num_bs, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      mbe_destroy(env);
+      return fail("mbe_create: bs_class upload failed: %s", cudaGetErrorString(e));
+    }
+    a.bs_class = env->d_bs_class;
+  }
+  env->smem = mbe::smem_bytes(gym, ma, a.epb, a.U, a.B, a.F, a.bs_per_env);
+  env->grid = (a.E + a.epb - 1) / a.epb;
+  if (env->smem > 200 * 1024) {
+    mbe_destroy(env);
+    return fail("mbe_create: needs %zu bytes of shared memory per block", env->smem);
+  }
+  const void* fn = gym ? (ma ? (const void*)mbe::step_kernel<1, 1> : (const void*)mbe::step_kernel<1, 0>)
+                       : (const void*)mbe::step_kernel<0, 0>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem);
+  if (e != cudaSuccess) {
+    mbe_destroy(env);
+    return fail("mbe_create: cudaFuncSetAttribute(%zu B smem): %s", env->smem, cudaGetErrorString(e));
+  }
+  *out = env;
+  return 0;
+}
+
+void mbe_destroy(mbe_env* env) {
+  if (!env) return;
+  for (double* p : env->luts) cudaFree(p);
+  if (env->d_bs_class) cudaFree(env->d_bs_class);
+  delete env;
+}
+
+int mbe_bind(mbe_env* env, const mbe_buffers* b) {
+  if (!env || !b) return fail("mbe_bind: null argument");
+  const bool gym = env->cfg.mode == MBE_MODE_GYM;
+  if (!b->pos || !b->wp || !b->t || !b->episode || !b->bs_xy || !b->utility || !b->done)
+    return fail("mbe_bind: pos, wp, t, episode, bs_xy, utility and done are required");
+  if (gym && (!b->conn || !b->actions || !b->obs || !b->reward))
+    return fail("mbe_bind: GYM mode needs conn, actions, obs and reward");
+  if (!gym && !b->assoc) return fail("mbe_bind: FORK mode needs assoc");
+  if (env->cfg.bs_random_max > 0 && !b->nbs) return fail("mbe_bind: random BS layouts need nbs");
+  if (b->inj_wp && (!b->wp_cnt || b->inj_k <= 0)) return fail("mbe_bind: inj_wp needs wp_cnt and inj_k > 0");
+  if (((uintptr_t)b->pos | (uintptr_t)b->wp | (uintptr_t)b->bs_xy | (uintptr_t)b->inj_wp) & 3)
+    return fail("mbe_bind: int16 pair buffers must be 4-byte aligned");
+  if (b->metrics && ((uintptr_t)b->metrics & 15)) return fail("mbe_bind: metrics must be 16-byte aligned");
+  if (b->rate && ((uintptr_t)b->rate & 7)) return fail("mbe_bind: rate must be 8-byte aligned");
+  env->bufs = *b;
+  mbe::StepArgs& a = env->args;
+  a.pos = reinterpret_cast<uint32_t*>(b->pos);
+  a.wp = reinterpret_cast<uint32_t*>(b->wp);
+  a.t = b->t;
+  a.episode = b->episode;
+  a.bs_xy = reinterpret_cast<uint32_t*>(b->bs_xy);
+  a.nbs = b->nbs;
+  a.conn = b->conn;
+  a.assoc = b->assoc;
+  a.actions = b->actions;
+  a.rate = b->rate;
+  a.utility = b->utility;
+  a.obs = b->obs;
+  a.reward = b->reward;
+  a.done = b->done;
+  a.metrics = b->metrics;
+  a.dbg_snr = b->dbg_snr;
+  a.inj_wp = reinterpret_cast<const uint32_t*>(b->inj_wp);
+  a.wp_cnt = b->wp_cnt;
+  a.inj_k = b->inj_k;
+  a.obs_bulk_ok = b->obs && (((uintptr_t)b->obs & 15) == 0);
+  env->bound = true;
+  return 0;
+}
+
+static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* stream) {
+  if (!env) return fail("null handle");
+  if (!env->bound) return fail("mbe_bind has not been called");
+  mbe::StepArgs a = env->args;
+  a.op = op;
+  a.phases = phases;
+  a.reset_mask = mask;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool gym = env->cfg.mode == MBE_MODE_GYM, ma = env->cfg.handler == MBE_HANDLER_MA;
+  if (!gym)
+    mbe::step_kernel<0, 0><<<env->grid, mbe::kThreads, env->smem, st>>>(a);
+  else if (!ma)
+    mbe::step_kernel<1, 0><<<env->grid, mbe::kThreads, env->smem, st>>>(a);
+  else
+    mbe::step_kernel<1, 1><<<env->grid, mbe::kThreads, env->smem, st>>>(a);
+  MBE_CUDA(cudaGetLastError());
+  env->launches += 1;
+  return 0;
+}
+
+int mbe_reset(mbe_env* env, const uint8_t* env_mask, void* stream) {
+  return launch(env, mbe::OP_RESET, 0, env_mask, stream);
+}
+
+int mbe_step(mbe_env* env, void* stream) { return launch(env, mbe::OP_STEP, MBE_PHASE_ALL, nullptr, stream); }
+
+int mbe_stage(mbe_env* env, int phase_mask, void* stream) {
+  if (phase_mask <= 0 || phase_mask > MBE_PHASE_ALL) return fail("mbe_stage: bad phase mask %d", phase_mask);
+  return launch(env, mbe::OP_STEP, phase_mask, nullptr, stream);
+}
+
+int mbe_observe(mbe_env* env, void* stream) {
+  if (env && env->cfg.mode != MBE_MODE_GYM) return fail("mbe_observe: GYM mode only");
+  return launch(env, mbe::OP_OBSERVE, 0, nullptr, stream);
+}
+
+int mbe_channel(mbe_env* env, float* out_snr, uint32_t* out_elig, void* stream) {
+  if (!env) return fail("null handle");
+  if (!env->bound) return fail("mbe_bind has not been called");
+  const mbe::StepArgs& a = env->args;
+  const size_t total = (size_t)a.E * a.U;
+  const int grid = (int)((total + mbe::kThreads - 1) / mbe::kThreads);
+  const size_t smem = 4 * (size_t)(a.bs_per_env ? (mbe::kThreads / a.U + 2) * a.B : a.B) + a.B + 16;
+  mbe::channel_kernel<<<grid, mbe::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(a, out_snr, out_elig);
+  MBE_CUDA(cudaGetLastError());
+  env->launches += 1;
+  return 0;
+}
+
+int64_t mbe_launch_count(const mbe_env* env) { return env ? env->launches : 0; }
+
+int mbe_step_host(mbe_env* env, const int32_t* actions_host, float* obs_host, float* reward_host,
+                  uint8_t* done_host, void* stream) {
+  if (!env) return fail("null handle");
+  if (!env->bound) return fail("mbe_bind has not been called");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const mbe::StepArgs& a = env->args;
+  const bool gym = env->cfg.mode == MBE_MODE_GYM, ma = env->cfg.handler == MBE_HANDLER_MA;
+  const size_t EU = (size_t)a.E * a.U;
+  if (actions_host) {
+    if (!gym) return fail("mbe_step_host: actions only exist in GYM mode");
+    MBE_CUDA(cudaMemcpyAsync(const_cast<int32_t*>(env->bufs.actions), actions_host, EU * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (int rc = mbe_step(env, stream)) return rc;
+  if (obs_host) {
+    if (!gym) return fail("mbe_step_host: obs only exists in GYM mode");
+    MBE_CUDA(cudaMemcpyAsync(obs_host, env->bufs.obs, EU * a.F * 4, cudaMemcpyDeviceToHost, st));
+  }
+  if (reward_host) {
+    if (!gym) return fail("mbe_step_host: reward only exists in GYM mode");
+    MBE_CUDA(cudaMemcpyAsync(reward_host, env->bufs.reward, (ma ? EU : (size_t)a.E) * 4, cudaMemcpyDeviceToHost, st));
+  }
+  if (done_host) MBE_CUDA(cudaMemcpyAsync(done_host, env->bufs.done, (size_t)a.E, cudaMemcpyDeviceToHost, st));
+  MBE_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

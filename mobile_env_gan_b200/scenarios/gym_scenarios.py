@@ -1,0 +1,44 @@
+"""Gymnasium-shaped scenarios ``mobile-{small,medium,large}-{central,ma}-v0``.
+
+The reference fork ships none of them (mobile_env/scenarios/__init__.py is empty); sizes follow
+BASELINE.json (small 3 BS x 5 UE, large 13 BS x 30 UE) and SURVEY.md section 8 (medium 4 x 15).
+Station coordinates are this build's own fixed integer layouts on the 200 x 200 map."""
+from __future__ import annotations
+
+from ..core.base import MComCore
+from ..core.entities import BaseStation, UserEquipment
+
+
+class _GymScenario(MComCore):
+    STATIONS = ()
+    NUM_UES = 0
+
+    @classmethod
+    def default_config(cls):
+        config = super().default_config()
+        config.update({"mode": "gym", "handler": "central"})
+        return config
+
+    def __init__(self, config=None, render_mode=None):
+        config = config or {}
+        base = self.default_config()
+        bs_cfg = dict(base["bs"]); bs_cfg.update(config.get("bs", {}))
+        ue_cfg = dict(base["ue"]); ue_cfg.update(config.get("ue", {}))
+        stations = [BaseStation(i, pos, **bs_cfg) for i, pos in enumerate(self.STATIONS)]
+        users = [UserEquipment(i, **ue_cfg) for i in range(self.NUM_UES)]
+        super().__init__(stations, users, config, render_mode)
+
+
+class MComSmall(_GymScenario):
+    STATIONS = ((110, 130), (65, 80), (120, 30))
+    NUM_UES = 5
+
+
+class MComMedium(_GymScenario):
+    STATIONS = ((50, 50), (150, 50), (50, 150), (150, 150))
+    NUM_UES = 15
+
+
+class MComLarge(_GymScenario):
+    STATIONS = tuple((20 + 45 * (i % 4) + (22 if (i // 4) % 2 else 0), 25 + 50 * (i // 4)) for i in range(13))
+    NUM_UES = 30

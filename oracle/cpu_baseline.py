@@ -1,0 +1,71 @@
+"""TEST/BENCH INFRASTRUCTURE ONLY -- times the CPU restatement of the reference's step on host
+cores (``cpu_baseline`` and ``--impl reference`` legs of bench.py).  The scalar port
+(``ScalarEnv``) runs per-entity Python loops exactly like the reference does
+(mobile_env/core/base.py:230-296), so its speed is the reference's speed class; the numbers it
+produces are a reported baseline, not a target."""
+from __future__ import annotations
+
+import multiprocessing as mp
+import os
+import time
+
+import numpy as np
+
+from oracle import mbe_oracle as orc
+
+WORKLOADS = {
+    # name: (bs_xy, num_ues, mode, handler, velocity)
+    "mobile-small-central-v0": ([(110, 130), (65, 80), (120, 30)], 5, "gym", "central", 1.5),
+    "mobile-medium-central-v0": ([(50, 50), (150, 50), (50, 150), (150, 150)], 15, "gym", "central", 1.5),
+    "mobile-medium-ma-v0": ([(50, 50), (150, 50), (50, 150), (150, 150)], 15, "gym", "ma", 1.5),
+    "mobile-large-central-v0": (
+        [(20 + 45 * (i % 4) + (22 if (i // 4) % 2 else 0), 25 + 50 * (i // 4)) for i in range(13)],
+        30, "gym", "central", 1.5),
+}
+
+
+def _worker(args):
+    workload, seconds, seed = args
+    bs, U, mode, handler, vel = WORKLOADS[workload]
+    p = orc.Params(velocity=vel)
+    rng = np.random.default_rng(seed)
+    env = orc.ScalarEnv(p, bs, U, wp_source=lambda u, k: (int(rng.uniform(0, p.width)), int(rng.uniform(0, p.height))))
+
+    def fresh():
+        env.reset([(int(rng.uniform(0, p.width)), int(rng.uniform(0, p.height))) for _ in range(U)])
+
+    fresh()
+    B = len(bs)
+    steps = 0
+    t0 = time.perf_counter()
+    while True:
+        if mode == "gym":
+            _, _, done, _ = env.step_gym(rng.integers(0, B + 1, size=U), handler)
+        else:
+            done = env.step_fork()["done"]
+        steps += 1
+        if done:
+            fresh()
+        if steps % 8 == 0 and time.perf_counter() - t0 >= seconds:
+            break
+    return steps, time.perf_counter() - t0
+
+
+def run(workload: str, seconds: float = 5.0, procs: int | None = None):
+    """Steps independent envs of ``workload`` on ``procs`` host processes for ``seconds`` each.
+    Returns dict(value=env-steps/s aggregate, cores, single_core, sample)."""
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_worker, [(workload, seconds, 1000 + i) for i in range(procs)])
+    total = sum(s for s, _ in res)
+    wall = max(t for _, t in res)
+    return {
+        "value": total / wall,
+        "unit": "env-steps/s",
+        "cores": procs,
+        "kind": "port",
+        "single_core": float(np.mean([s / t for s, t in res])),
+        "sample": f"{procs} procs x {seconds:.0f} s of {workload} (scalar port of MComCore.step, "
+                  f"one env per process, {total} env-steps)",
+    }

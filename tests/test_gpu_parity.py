@@ -1,0 +1,292 @@
+"""Parity of the CUDA path (through the C ABI, via the host mirror of MComCore) against the
+oracle.  Bars (BASELINE.json north_star):
+  * positions, association / connection sets, done flags, counts: bit-exact;
+  * rates: bit-exact in FP64 (the per-link Shannon rate is a host-folded FP64 table indexed by
+    the integer d^2, then split and rounded in FP64 on the device);
+  * SNR, utility, obs, reward, mean metrics: |a-b| <= RTOL*|b| + ATOL with RTOL = 1e-5 and
+    ATOL = 1e-6 (FP32 vs numpy FP64; the absolute term only matters at zero crossings of the
+    [-1,1]-scaled utilities)."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, golden_waypoints, load_golden
+from mirror import Mirror, conn_bits
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+
+torch = pytest.importorskip("torch")
+
+
+def _mods():
+    from mobile_env_gan_b200.core.base import MComCore
+    from mobile_env_gan_b200.core.entities import BaseStation, UserEquipment
+
+    return MComCore, BaseStation, UserEquipment
+
+
+def make_env(bs_xy, nue, config):
+    MComCore, BaseStation, UserEquipment = _mods()
+    cfg = MComCore.default_config()
+    from mobile_env_gan_b200.core.util import deep_dict_merge
+
+    cfg = deep_dict_merge(cfg, config)
+    stations = [BaseStation(i, tuple(xy), **cfg["bs"]) for i, xy in enumerate(bs_xy)] if bs_xy is not None else []
+    users = [UserEquipment(i, **cfg["ue"]) for i in range(nue)]
+    return MComCore(stations, users, config)
+
+
+def close(a, b, what=""):
+    np.testing.assert_allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64),
+                               rtol=RTOL, atol=ATOL, err_msg=what)
+
+
+def golden_config(rec, extra=None):
+    p = rec["params"]
+    cfg = {
+        "width": p["width"], "height": p["height"], "EP_MAX_TIME": p["ep_time"],
+        "arrival_params": {"ep_time": p["ep_time"]},
+        "bs": {"bw": p["bw"], "freq": p["freq"], "tx": p["tx"], "height": p["bs_height"]},
+        "ue": {"velocity": p["velocity"], "snr_tr": p["snr_tr"], "noise": p["noise"], "height": p["ue_height"]},
+        "utility_params": {"lower": p["util_lower"], "upper": p["util_upper"], "coeffs": tuple(p["util_coeffs"])},
+    }
+    cfg.update(extra or {})
+    return cfg
+
+
+# ------------------------------------------------------------------ reference trajectories
+@pytest.mark.parametrize("name", golden_names())
+def test_fork_replays_reference_trajectory(name):
+    """Injects the reference's positions and waypoints (tests/golden, generated from the
+    unmodified reference) and compares every step of the episode."""
+    rec = load_golden(name)
+    E = 5  # replicas of the same episode: also checks envs are independent of their slot
+    U = len(rec["init_pos"])
+    env = make_env(rec["bs_xy"], U, golden_config(rec, {"num_envs": E, "mode": "fork"}))
+    snr_dbg = env.enable_debug_snr()
+    seq = golden_waypoints(rec)
+    K = max(1, max(len(s) for s in seq))
+    wp = np.zeros((E, U, K, 2), dtype=np.int16)
+    for u, s in enumerate(seq):
+        for k, w in enumerate(s):
+            wp[:, u, k] = w
+    env.reset()
+    env.inject_waypoints(wp)
+    env.set_positions(np.broadcast_to(np.array(rec["init_pos"]), (E, U, 2)).copy())
+    for k, g in enumerate(rec["steps"]):
+        env.step(0, k)
+        for e in (0, E - 1):
+            assert env.pos[e].cpu().tolist() == g["pos"], (name, k)
+            assert env.assoc[e].cpu().tolist() == g["conn"], (name, k)
+            assert env.rate[e].cpu().tolist() == g["rate"], (name, k)  # FP64, bit-exact
+            close(env.utility_scaled[e].cpu(), g["utility"], f"{name} utility step {k}")
+            assert bool(env.done[e]) == g["done"]
+            m = env.metrics[e].cpu().tolist()
+            assert m[0] == g["n_connections"] and m[1] == g["n_connected"]
+            close(m[2], g["mean_utility"], "mean utility")
+            close(m[3], g["mean_datarate"], "mean datarate")
+            got = snr_dbg[e].cpu().numpy().astype(np.float64)
+            ref = np.array(g["snr"])
+            fin = ref < 3e38  # d = 0 gives 3.8e53 in FP64 -> inf in FP32 on both sides
+            close(got[fin], ref[fin], f"{name} snr step {k}")
+            assert np.all(np.isinf(got[~fin]))
+
+
+# --------------------------------------------------------------------- FORK, Philox driven
+@pytest.mark.parametrize("autoreset", [False, True])
+def test_fork_random_layouts_match_oracle(autoreset):
+    """MComCustom-style: random BS layout per env and episode, Philox waypoints."""
+    from mobile_env_gan_b200.scenarios import MComCustom
+
+    E = 777  # not a multiple of the envs per block
+    env = MComCustom(config={"num_envs": E, "autoreset": autoreset, "env_offset": 12345,
+                             "movement_params": {"reset_rng_episode": False}})
+    mir = Mirror(env)
+    env.reset()
+    mir.reset()
+    assert np.array_equal(env.pos.cpu().numpy(), mir.pos)
+    assert np.array_equal(env.nbs.cpu().numpy(), mir.nbs)
+    assert np.array_equal(env.bs_xy.cpu().numpy(), mir.bs)
+    for k in range(45 if autoreset else 20):
+        env.step(0, k)
+        out = mir.step_fork()
+        assert np.array_equal(env.assoc.cpu().numpy(), out["assoc"]), k
+        assert np.array_equal(env.rate.cpu().numpy(), out["rate"]), k
+        assert np.array_equal(env.done.cpu().numpy().astype(bool), out["done"]), k
+        assert np.array_equal(env.pos.cpu().numpy(), out["pos_after"]), k
+        assert np.array_equal(env.t.cpu().numpy(), mir.t)
+        assert np.array_equal(env.episode.cpu().numpy(), mir.episode)
+        assert np.array_equal(env.bs_xy.cpu().numpy(), mir.bs)
+        close(env.utility_scaled.cpu(), out["utility"], f"utility step {k}")
+        m = env.metrics.cpu().numpy()
+        assert np.array_equal(m[:, 1], out["n_connected"])
+        close(m[:, 2], out["mean_utility"])
+        close(m[:, 3], out["mean_datarate"])
+
+
+# ----------------------------------------------------------------------------- GYM mode
+SCENARIOS = {
+    "small": ([(110, 130), (65, 80), (120, 30)], 5),
+    "medium": ([(50, 50), (150, 50), (50, 150), (150, 150)], 15),
+    "large": ([(20 + 45 * (i % 4), 25 + 50 * (i // 4)) for i in range(13)], 30),
+    "wide": ([(7 * i % 200, 13 * i % 200) for i in range(32)], 32),
+    "one": ([(100, 100)], 1),
+}
+
+
+@pytest.mark.parametrize("handler", ["central", "ma"])
+@pytest.mark.parametrize("scen", list(SCENARIOS))
+@pytest.mark.parametrize("autoreset", [False, True])
+def test_gym_matches_oracle(scen, handler, autoreset):
+    bs, U = SCENARIOS[scen]
+    E = 301
+    cfg = {"num_envs": E, "mode": "gym", "handler": handler, "autoreset": autoreset,
+           "EP_MAX_TIME": 12, "arrival_params": {"ep_time": 12}, "ue": {"velocity": 7.5}, "seed": 99,
+           "movement_params": {"reset_rng_episode": False}}
+    env = make_env(bs, U, cfg)
+    mir = Mirror(env)
+    obs, _ = env.reset()
+    ref_obs = mir.reset()
+    B = len(bs)
+    close(obs.cpu().numpy().reshape(E, U, -1), ref_obs, "reset obs")
+    rng = np.random.default_rng(5)
+    for k in range(30 if autoreset else 12):
+        acts = rng.integers(0, B + 1, size=(E, U)).astype(np.int32)
+        obs, rew, term, trunc, info = env.step(torch.from_numpy(acts).to(env.device))
+        out = mir.step_gym(acts)
+        assert np.array_equal(env.conn.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, conn_bits(out["conn_after"])), k
+        assert np.array_equal(env.pos.cpu().numpy(), out["pos_after"]), k
+        assert np.array_equal(trunc.cpu().numpy(), out["done"]), k
+        assert not term.any()
+        assert np.array_equal(env.rate.cpu().numpy(), out["rate"]), k
+        close(env.utility_scaled.cpu(), out["utility"], f"utility {k}")
+        close(rew.cpu(), out["reward"], f"reward {k}")
+        close(obs.cpu().numpy().reshape(E, U, -1), out["obs"], f"obs {k}")
+        m = env.metrics.cpu().numpy()
+        assert np.array_equal(m[:, 0], out["n_connections"]) and np.array_equal(m[:, 1], out["n_connected"])
+        close(m[:, 3], out["mean_datarate"])
+
+
+def test_gym_random_layouts_autoreset():
+    """GYM on per-env random layouts (5..10 live BSs in 10 slots) with same-step autoreset."""
+    E, U = 200, 7
+    cfg = {"num_envs": E, "mode": "gym", "handler": "ma", "autoreset": True, "bs_random": (5, 10),
+           "max_bs": 10, "EP_MAX_TIME": 6, "arrival_params": {"ep_time": 6}, "ue": {"velocity": 10}}
+    env = make_env(None, U, cfg)
+    mir = Mirror(env)
+    obs, _ = env.reset()
+    close(obs.cpu().numpy(), mir.reset(), "reset obs")
+    rng = np.random.default_rng(11)
+    for k in range(20):
+        acts = rng.integers(0, 11, size=(E, U)).astype(np.int32)
+        obs, rew, _, trunc, _ = env.step(torch.from_numpy(acts).to(env.device))
+        out = mir.step_gym(acts)
+        assert np.array_equal(env.conn.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, conn_bits(out["conn_after"])), k
+        assert np.array_equal(env.bs_xy.cpu().numpy(), mir.bs)
+        assert np.array_equal(env.rate.cpu().numpy(), out["rate"]), k
+        close(rew.cpu(), out["reward"], f"reward {k}")
+        close(obs.cpu().numpy(), out["obs"], f"obs {k}")
+
+
+# ------------------------------------------------------------------ stages and channel
+@pytest.mark.parametrize("mode", ["fork", "gym"])
+def test_split_phases_equal_fused_step(mode):
+    from mobile_env_gan_b200 import _lib
+
+    bs, U = SCENARIOS["medium"]
+    cfg = {"num_envs": 256, "mode": mode, "handler": "ma", "ue": {"velocity": 4}}
+    a, b = make_env(bs, U, cfg), make_env(bs, U, cfg)
+    a.reset(), b.reset()
+    rng = np.random.default_rng(3)
+    order = [1, 2, 4] if mode == "fork" else [2, 1, 4, 8]
+    for k in range(20):
+        if mode == "gym":
+            acts = torch.from_numpy(rng.integers(0, 5, size=(256, U)).astype(np.int32)).cuda()
+            a.step(acts)
+            b.actions.copy_(acts)
+        else:
+            a.step(0, k)
+        for ph in order:
+            b.stage(ph)
+        for name in ("pos", "wp", "t", "rate", "utility_scaled", "done", "conn", "assoc", "obs", "reward", "metrics"):
+            ta, tb = getattr(a, name), getattr(b, name)
+            if ta is not None:
+                assert torch.equal(ta, tb), (name, k)
+    assert _lib.PHASE_ALL == 15
+
+
+def test_channel_kernel_matches_oracle():
+    from oracle import mbe_oracle as orc
+
+    bs, U = SCENARIOS["large"]
+    env = make_env(bs, U, {"num_envs": 1000, "mode": "fork", "ue": {"velocity": 10}})
+    mir = Mirror(env)
+    env.reset(), mir.reset()
+    for k in range(3):
+        env.step(0, k), mir.step_fork()
+    snr, elig = env.channel_snr(want_elig=True)
+    ref, _ = orc.batch_snr(mir.p, mir.pos, mir.bs)
+    close(snr.cpu(), ref, "snr")
+    assert np.array_equal(elig.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, conn_bits(ref > mir.p.snr_tr))
+
+
+# ------------------------------------------------------------------------- full size
+def test_full_size_medium_properties_and_sharding():
+    """BASELINE configs[1] size (65,536 envs): sharded halves reproduce the whole, and the
+    size-independent invariants of the domain hold."""
+    import mobile_env_gan_b200 as mbe
+
+    E = 65536
+    whole = mbe.make("mobile-medium-central-v0", num_envs=E, autoreset=True)
+    lo = mbe.make("mobile-medium-central-v0", num_envs=E // 2, autoreset=True)
+    hi = mbe.make("mobile-medium-central-v0", num_envs=E // 2, autoreset=True, env_offset=E // 2)
+    for env in (whole, lo, hi):
+        env.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    U, B = 15, 4
+    for k in range(25):
+        acts = torch.randint(0, B + 1, (E, U), generator=g, device="cuda", dtype=torch.int32)
+        _, elig_pre = whole.channel_snr(want_elig=True)
+        obs, rew, _, trunc, _ = whole.step(acts)
+        o1, r1, _, t1, _ = lo.step(acts[: E // 2])
+        o2, r2, _, t2, _ = hi.step(acts[E // 2:])
+        assert torch.equal(obs, torch.cat([o1, o2])) and torch.equal(rew, torch.cat([r1, r2]))
+        assert torch.equal(trunc, torch.cat([t1, t2]))
+        assert bool(trunc.all()) == ((k + 1) % 20 == 0) and bool(trunc.any()) == bool(trunc.all())
+        assert float(obs.min()) >= -1.0 and float(obs.max()) <= 1.0
+        assert float(rew.min()) >= -1.0 and float(rew.max()) <= 1.0
+        assert int((whole.conn & ~elig_pre).count_nonzero()) == 0  # links only where connectable (base.py:221-227)
+        con = whole.conn != 0
+        assert bool((whole.rate[con] > 0).all()) and bool((whole.rate[~con] == 0).all())
+        o = obs.view(E, U, 2 * B + 1)
+        assert torch.equal(o[:, :, :B] > 0, ((whole.conn.unsqueeze(-1) >> torch.arange(B, device="cuda")) & 1) > 0)
+        assert float(o[:, :, B:2 * B].max(dim=2).values.min()) == 1.0  # the best BS has ratio 1
+
+
+def test_step_host_roundtrip():
+    import mobile_env_gan_b200 as mbe
+
+    E, U, B = 4096, 15, 4
+    a = mbe.make("mobile-medium-central-v0", num_envs=E)
+    b = mbe.make("mobile-medium-central-v0", num_envs=E)
+    a.reset(), b.reset()
+    acts = torch.randint(0, B + 1, (E, U), dtype=torch.int32).pin_memory()
+    obs_h = torch.empty(E, U * (2 * B + 1), dtype=torch.float32).pin_memory()
+    rew_h = torch.empty(E, dtype=torch.float32).pin_memory()
+    done_h = torch.empty(E, dtype=torch.uint8).pin_memory()
+    a.step_host(acts, obs_h, rew_h, done_h)
+    obs, rew, _, trunc, _ = b.step(acts.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(obs_h, obs.cpu()) and torch.equal(rew_h, rew.cpu()) and torch.equal(done_h.bool(), trunc.cpu())
+
+
+def test_errors_are_loud():
+    MComCore, BaseStation, UserEquipment = _mods()
+    from mobile_env_gan_b200._lib import MbeError
+
+    with pytest.raises(MbeError):
+        make_env(SCENARIOS["small"][0], 40, {"num_envs": 4})  # U > 32 has no kernel yet
+    env = make_env(SCENARIOS["small"][0], 5, {"num_envs": 4})
+    with pytest.raises(RuntimeError):
+        env.step(0, 0)  # reset() first

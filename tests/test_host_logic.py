@@ -1,0 +1,193 @@
+"""CPU-side checks: host folding vs the oracle's scalar chain, config/plugin surface, the
+C-ABI library (loads, exports every symbol of include/mbe.h; no compute without a GPU) and the
+multi-rank sharding logic on gloo (world_size 2)."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mbe_oracle as orc
+from mobile_env_gan_b200 import _lib
+from mobile_env_gan_b200.core.base import MComCore
+from mobile_env_gan_b200.core.channels import LogDistance, OkumuraHata
+from mobile_env_gan_b200.core.entities import BaseStation, UserEquipment
+from mobile_env_gan_b200.core.movement import Movement, RandomWaypointMovement
+from mobile_env_gan_b200.core.schedules import RateFair
+from mobile_env_gan_b200.core.util import deep_dict_merge
+from mobile_env_gan_b200.sharding import shard_envs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def entities(tx=40.0, h=1.6, v=1.5):
+    bs = BaseStation(0, (10, 20), 9e6, 2500, tx, 50)
+    ue = UserEquipment(0, v, 2e-8, 1e-9, h)
+    return bs, ue
+
+
+@pytest.mark.parametrize("tx,h", [(40.0, 1.6), (30.0, 1.8), (30.0, 1.5), (46.0, 1.6), (5.0, 1.6)])
+def test_fold_matches_oracle_scalar_chain(tx, h):
+    bs, ue = entities(tx, h)
+    f = OkumuraHata().fold(bs, ue, 200 * 200 * 2)
+    p = orc.Params(tx=tx, ue_height=h)
+    d2max = f["d2max"]
+    if d2max >= 0:
+        assert orc.snr_of(p, math.sqrt(d2max)) > p.snr_tr
+    assert not (orc.snr_of(p, math.sqrt(d2max + 1)) > p.snr_tr)
+    # the rate table is the reference's Channel.datarate, bit for bit
+    for d2 in list(range(0, min(d2max, 50) + 1)) + list(range(max(d2max - 50, 0), d2max + 1)):
+        assert f["rate_lut"][d2] == orc.datarate_of(p, orc.snr_of(p, math.sqrt(d2)))
+    # log-domain constants reproduce the FP64 SNR
+    for d2 in (1, 2, 100, 5000, 19362, 79999):
+        want = math.log2(orc.snr_of(p, math.sqrt(d2)))
+        assert f["l0"] - f["k"] * math.log2(d2) == pytest.approx(want, abs=1e-9)
+    assert f["l_zero"] == pytest.approx(math.log2(orc.snr_of(p, 0.0)), abs=1e-9)
+
+
+def test_default_cutoff_is_the_surveyed_one():
+    bs, ue = entities()
+    assert OkumuraHata().fold(bs, ue, 80002)["d2max"] == 19362
+
+
+def test_channel_scalar_surface_matches_reference_formulas():
+    bs, ue = entities(30.0, 1.8)
+    ue.x, ue.y = 81.9, 109.2  # truncated to (81, 109) like entities.py:52-54
+    ch = OkumuraHata()
+    p = orc.Params(tx=30.0, ue_height=1.8)
+    d = orc.int_point_dist(10, 20, 81.9, 109.2)
+    assert ch.power_loss(bs, ue) == orc.power_loss(p, d)
+    assert ch.calculateSNR(bs, ue) == orc.snr_of(p, d)
+    assert ch.datarate(bs, ue, 1e-6) == orc.datarate_of(p, 1e-6) and ch.datarate(bs, ue, 1e-9) == 0.0
+    assert LogDistance(a=40, c=30).fold(bs, ue, 80000)["k"] == pytest.approx(1.5)
+
+
+@pytest.mark.parametrize("v,want", [(10, 100), (1.5, 2), (0.5, 0), (1.0, 1), (7.5, 56), (2 ** 0.5, 2)])
+def test_move_threshold(v, want):
+    m = RandomWaypointMovement(width=200, height=200, seed=1, reset_rng_episode=True)
+    got = m.device_params(v)["move_d2max"]
+    assert got == want
+    assert math.sqrt(got) <= v < math.sqrt(got + 1) or (got == 0 and v < 1)
+
+
+def test_config_merge_seeding_and_plan():
+    cfg = MComCore.default_config()
+    assert cfg["bs"] == {"bw": 9e6, "freq": 2500, "tx": 40, "height": 50}  # base.py:117
+    assert cfg["ue"] == {"velocity": 1.5, "snr_tr": 2e-8, "noise": 1e-9, "height": 1.6}
+    cfg = deep_dict_merge(cfg, {"ue": {"velocity": 10}, "num_envs": 8, "mode": "gym", "handler": "ma"})
+    cfg = MComCore.seeding(cfg)
+    assert cfg["movement_params"]["seed"] == 2028 and cfg["arrival_params"]["seed"] == 2025  # base.py:155-170
+    stations = [BaseStation(i, (10 * i, 5), **cfg["bs"]) for i in range(4)]
+    stations[2].tx_power = 30  # second radio class
+    users = [UserEquipment(i, **cfg["ue"]) for i in range(15)]
+    plan = MComCore.build_plan(stations, users, cfg)
+    assert (plan.num_envs, plan.num_ues, plan.num_bs, plan.feature_size) == (8, 15, 4, 17)
+    assert plan.seed == 2028 and plan.ep_time == 20 and plan.move_d2max == 100
+    assert plan.bs_class.tolist() == [0, 0, 1, 0] and len(plan.classes) == 2
+    assert plan.classes[0]["d2max"] == 19362 and plan.classes[1]["d2max"] < 19362
+    assert plan.bs_xy.tolist() == [[0, 5], [10, 5], [20, 5], [30, 5]]
+
+
+def test_unsupported_plugins_fail_loudly():
+    cfg = MComCore.seeding(deep_dict_merge(MComCore.default_config(), {"scheduler": RateFair}))
+    users = [UserEquipment(0, **cfg["ue"])]
+    stations = [BaseStation(0, (1, 1), **cfg["bs"])]
+    with pytest.raises(NotImplementedError):
+        MComCore.build_plan(stations, users, cfg)
+
+    class Teleport(Movement):
+        def move(self, ue):
+            return 0, 0
+
+    cfg = MComCore.seeding(deep_dict_merge(MComCore.default_config(), {"movement": Teleport}))
+    with pytest.raises(NotImplementedError):
+        MComCore.build_plan(stations, users, cfg)
+    users2 = users + [UserEquipment(1, velocity=3, snr_tr=2e-8, noise=1e-9, height=1.6)]
+    cfg = MComCore.seeding(MComCore.default_config())
+    with pytest.raises(NotImplementedError):
+        MComCore.build_plan(stations, users2, cfg)
+
+
+def test_library_exports_every_declared_symbol():
+    """include/mbe.h is the contract: each prototype must be exported by libmbe.so."""
+    header = open(os.path.join(ROOT, "include", "mbe.h")).read()
+    declared = set(re.findall(r"\b(mbe_[a-z_]+)\s*\(", header))
+    declared -= {"mbe_create"} - {"mbe_create"}  # keep all
+    assert {name for name, _, _ in _lib.SYMBOLS} == declared
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mbe_abi_version() == _lib.MBE_ABI_VERSION
+    assert b"sm_100a" in lib.mbe_build_info()
+    # struct sizes the binding assumes (LP64)
+    assert ctypes.sizeof(_lib.BsClass) == 40
+    assert ctypes.sizeof(_lib.Buffers) == 18 * 8 + 8
+
+
+def test_library_rejects_bad_configs_without_a_gpu():
+    lib = _lib.load()
+    cfg = _lib.Config()
+    handle = ctypes.c_void_p()
+    assert lib.mbe_create(ctypes.byref(cfg), ctypes.byref(handle)) != 0
+    assert b"abi_version" in lib.mbe_last_error()
+    cfg.abi_version = _lib.MBE_ABI_VERSION
+    cfg.num_envs, cfg.num_ues, cfg.num_bs = 4, 64, 4
+    assert lib.mbe_create(ctypes.byref(cfg), ctypes.byref(handle)) != 0
+    assert b"num_ues" in lib.mbe_last_error()
+    assert lib.mbe_step(None, None) != 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_cpu_fallback():
+    import mobile_env_gan_b200 as mbe
+
+    with pytest.raises(_lib.MbeError):
+        mbe.make("mobile-small-central-v0", num_envs=2)
+
+
+def test_shard_envs_partitions_exactly():
+    for total, world in [(65536, 8), (1000, 3), (7, 8), (262144, 4)]:
+        spans = [shard_envs(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+        for (o0, c0), (o1, _) in zip(spans, spans[1:]):
+            assert o0 + c0 == o1
+        assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def _gloo_worker(rank, world, port, total, q):
+    import torch.distributed as dist
+
+    from mobile_env_gan_b200.sharding import gather_episode_stats, sharded_config
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    cfg = sharded_config(total)
+    ids = torch.arange(cfg["env_offset"], cfg["env_offset"] + cfg["num_envs"], dtype=torch.float32)
+    stats = torch.stack([ids, ids * 2], dim=1)
+    full = gather_episode_stats(stats, total)
+    q.put((rank, cfg, full.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_two_ranks_shard_and_gather():
+    import torch.multiprocessing as mp
+
+    total, world = 11, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [[float(i), float(2 * i)] for i in range(total)]
+    offsets = sorted(cfg["env_offset"] for _, cfg, _ in got)
+    assert offsets == [0, 6]
+    for _, _, full in got:
+        assert full == want
