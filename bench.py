@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--preheat-seconds", type=float, default=0.3)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -215,7 +216,7 @@ def main():
             raw_steps(n - done)
 
         # preheat (untimed) so that clocks are up, then W warm-up steps
-        t_end = time.perf_counter() + 0.3
+        t_end = time.perf_counter() + args.preheat_seconds
         while time.perf_counter() < t_end:
             run_steps(chunk)
             torch.cuda.synchronize()

@@ -21,7 +21,8 @@
  *   wp       int16 [E,U,2]   current waypoint; x < 0 = none (movement.py:44-47,54-56)
  *   t        int32 [E]       step clock of the episode (base.py:280, "time")
  *   episode  int32 [E]       episode counter (-1 before the first reset)
- *   bs_xy    int16 [B,2] or [E,B,2]  int-truncated BS coordinates (entities.py:24-26)
+ *   bs_xy    int16 [B,2] or [E,B,2]  int-truncated BS coordinates (entities.py:24-26); a shared
+ *                            [B,2] layout is read once by mbe_bind (re-bind after editing it)
  *   nbs      int32 [E]       live BS slots per env (random layouts, custom.py:68-77) or NULL
  *   conn     uint32 [E,U,MW] GYM: connection bitmask (bs2ue_connections, base.py:76)
  *   assoc    int32 [E,U]     FORK: BS index the UE is attached to, -1 = none (base.py:236-241)
@@ -50,6 +51,8 @@ enum { MBE_HANDLER_CENTRAL = 0, MBE_HANDLER_MA = 1 };
 enum { MBE_SCHED_RESOURCE_FAIR = 0 };
 enum { MBE_BS_SHARED = 0, MBE_BS_PER_ENV = 1 };
 enum { MBE_MAX_CLASSES = 8 };
+/* mbe_config.flags */
+enum { MBE_FLAG_GENERIC_KERNEL = 1 }; /* never use the shape-specialised fused kernels */
 
 /* phases of one step (bit mask for mbe_stage); the fused step runs all of them in one launch.
  * FORK order: MOVE, PRE, CLOCK.  GYM order: PRE, MOVE, CLOCK, POST. */
@@ -100,7 +103,7 @@ typedef struct mbe_config {
   double velocity;     /* ue.velocity (base.py:119) */
   double util_lower, util_upper, util_w1, util_w2, util_w3; /* utilities.py:30-55 */
   int32_t num_classes; /* 1..MBE_MAX_CLASSES */
-  int32_t reserved;
+  int32_t flags;       /* MBE_FLAG_* */
   mbe_bs_class classes[MBE_MAX_CLASSES];
   const uint8_t* bs_class; /* HOST [B] class id per BS slot, or NULL = all class 0 */
 } mbe_config;

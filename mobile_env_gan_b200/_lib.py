@@ -16,6 +16,7 @@ HANDLER_CENTRAL, HANDLER_MA = 0, 1
 SCHED_RESOURCE_FAIR = 0
 BS_SHARED, BS_PER_ENV = 0, 1
 MAX_CLASSES = 8
+FLAG_GENERIC_KERNEL = 1
 PHASE_MOVE, PHASE_PRE, PHASE_CLOCK, PHASE_POST, PHASE_ALL = 1, 2, 4, 8, 15
 
 
@@ -58,7 +59,7 @@ class Config(C.Structure):
         ("util_w2", C.c_double),
         ("util_w3", C.c_double),
         ("num_classes", C.c_int32),
-        ("reserved", C.c_int32),
+        ("flags", C.c_int32),
         ("classes", BsClass * MAX_CLASSES),
         ("bs_class", C.POINTER(C.c_uint8)),
     ]

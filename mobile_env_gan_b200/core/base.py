@@ -106,6 +106,7 @@ class MComCore:
             "autoreset": False,
             "bs_random": None,  # (min, max): draw a BS layout per env and episode (custom.py:68-77)
             "max_bs": None,  # BS slots when bs_random is used
+            "generic_kernel": False,  # True: never use the shape-specialised fused kernels
         }
 
     @classmethod
@@ -259,6 +260,7 @@ class MComCore:
         cfg.width, cfg.height, cfg.velocity = p.width, p.height, p.velocity
         cfg.util_lower, cfg.util_upper, cfg.util_w1, cfg.util_w2, cfg.util_w3 = p.utility
         cfg.num_classes = len(p.classes)
+        cfg.flags = _lib.FLAG_GENERIC_KERNEL if self.config.get("generic_kernel") else 0
         for i, c in enumerate(p.classes):
             lut = np.ascontiguousarray(c["rate_lut"], dtype=np.float64)
             self._keepalive.append(lut)
@@ -334,6 +336,7 @@ class MComCore:
         self.bs_xy.copy_(torch.as_tensor(bs_xy).to(device=self.device, dtype=torch.int16))
         if nbs is not None:
             self.nbs.copy_(torch.as_tensor(nbs).to(device=self.device, dtype=torch.int32))
+        self._bind()  # a shared layout is folded into the kernel parameters at bind time
 
     # ----------------------------------------------------------------------------- run ----
     def _stream(self):

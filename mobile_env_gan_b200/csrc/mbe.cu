@@ -11,6 +11,7 @@
 
 #include "../../include/mbe.h"
 #include "mbe_step.cuh"
+#include "mbe_step_spec.cuh"
 
 namespace {
 
@@ -44,7 +45,35 @@ struct mbe_env {
   size_t smem = 0;
   int grid = 0;
   int64_t launches = 0;
+  // specialised fused kernel for this shape (nullptr: generic kernel only)
+  void (*spec)(mbe::StepArgs) = nullptr;
+  size_t spec_smem = 0;
+  int spec_grid = 0;
 };
+
+namespace {
+
+struct SpecEntry {
+  int mode, handler, U, B, per_env;
+  void (*fn)(mbe::StepArgs);
+  size_t smem;
+};
+
+#define MBE_SPEC(MODE, HANDLER, U, B, PE)                                             \
+  SpecEntry {                                                                         \
+    MODE, HANDLER, U, B, PE, mbe::step_spec_kernel<MODE, HANDLER, U, B, (PE != 0)>,   \
+        mbe::spec_smem_bytes<HANDLER, U, B, (PE != 0)>(MODE == 1)                     \
+  }
+
+// shapes with a compile-time specialisation: the scenario sizes of BASELINE.json (small 3x5,
+// medium 4x15, large 13x30) and the fork's MComCustom (7 UEs, <= 10 random BSs per env)
+const SpecEntry kSpecs[] = {
+    MBE_SPEC(1, 0, 5, 3, 0),  MBE_SPEC(1, 1, 5, 3, 0),  MBE_SPEC(1, 0, 15, 4, 0),  MBE_SPEC(1, 1, 15, 4, 0),
+    MBE_SPEC(1, 0, 30, 13, 0), MBE_SPEC(1, 1, 30, 13, 0), MBE_SPEC(0, 0, 7, 10, 1), MBE_SPEC(0, 0, 5, 3, 0),
+    MBE_SPEC(0, 0, 15, 4, 0), MBE_SPEC(0, 0, 30, 13, 0), MBE_SPEC(1, 0, 7, 10, 1),  MBE_SPEC(1, 1, 7, 10, 1),
+};
+
+}  // namespace
 
 extern "C" {
 
@@ -111,6 +140,8 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   a.width = cfg->width;
   a.height = cfg->height;
   a.velocity = cfg->velocity;
+  a.velocity_f = (float)cfg->velocity;
+  a.tie_eps = (float)(cfg->velocity * 1e-6 + 1e-6);
   a.move_d2max = cfg->move_d2max;
   a.util_c = (float)(cfg->util_w1 * std::log(2.0) / std::log(cfg->util_w3));
   a.util_w2 = (float)cfg->util_w2;
@@ -127,18 +158,28 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     d.k_lo = (float)(h.k - (double)d.k_hi);
     d.l_zero = (float)h.l_zero;
     d.d2max = h.d2max;
-    d.lut = nullptr;
+    d.stride = h.d2max + 1;
+    d.lutn = nullptr;
     if (h.d2max >= 0) {
+      // lutn[(n-1)*stride + d2] = round(rate_lut[d2] / n, 2) in FP64 (schedules.py:20-22, base.py:435)
+      const int rows = a.U;
+      std::vector<double> tab((size_t)rows * d.stride);
+      for (int n = 1; n <= rows; ++n)
+        for (int i = 0; i < d.stride; ++i) {
+          volatile double share = h.rate_lut[i] / (double)n;
+          volatile double scaled = share * 100.0;
+          tab[(size_t)(n - 1) * d.stride + i] = std::nearbyint(scaled) / 100.0;
+        }
       double* p = nullptr;
-      size_t bytes = ((size_t)h.d2max + 1) * sizeof(double);
+      size_t bytes = tab.size() * sizeof(double);
       cudaError_t e = cudaMalloc(&p, bytes);
-      if (e == cudaSuccess) e = cudaMemcpy(p, h.rate_lut, bytes, cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMemcpy(p, tab.data(), bytes, cudaMemcpyHostToDevice);
       if (e != cudaSuccess) {
         mbe_destroy(env);
-        return fail("mbe_create: rate_lut upload failed: %s", cudaGetErrorString(e));
+        return fail("mbe_create: rate table upload failed: %s", cudaGetErrorString(e));
       }
       env->luts.push_back(p);
-      d.lut = p;
+      d.lutn = p;
     }
   }
   if (cfg->bs_class) {
@@ -155,6 +196,28 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     }
     a.bs_class = env->d_bs_class;
   }
+  for (int b = 0; b < mbe::kMaxSlots; ++b) {
+    const int c = (cfg->bs_class && b < cfg->num_bs) ? cfg->bs_class[b] : 0;
+    const mbe::ClassDev& d = a.cls[c];
+    mbe::SlotDev& sl = a.slot[b];
+    sl.x = sl.y = 0;  // coordinates of a shared layout arrive with mbe_bind (host copy of bs_xy)
+    sl.d2max = d.d2max;
+    sl.stride = d.stride;
+    sl.k = d.k_hi;
+    sl.l0 = d.l0_hi;
+    sl.l_zero = d.l_zero;
+    sl.pad = 0.0f;
+    sl.lutn = d.lutn;
+  }
+  if (!(cfg->flags & MBE_FLAG_GENERIC_KERNEL)) {
+    for (const SpecEntry& sp : kSpecs)
+      if (sp.mode == cfg->mode && (sp.handler == cfg->handler || !gym) && sp.U == a.U && sp.B == a.B &&
+          sp.per_env == a.bs_per_env) {
+        env->spec = sp.fn;
+        env->spec_smem = sp.smem;
+        break;
+      }
+  }
   env->smem = mbe::smem_bytes(gym, ma, a.epb, a.U, a.B, a.F, a.bs_per_env);
   env->grid = (a.E + a.epb - 1) / a.epb;
   if (env->smem > 200 * 1024) {
@@ -164,6 +227,9 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   const void* fn = gym ? (ma ? (const void*)mbe::step_kernel<1, 1> : (const void*)mbe::step_kernel<1, 0>)
                        : (const void*)mbe::step_kernel<0, 0>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem);
+  if (e == cudaSuccess && env->spec)
+    e = cudaFuncSetAttribute((const void*)env->spec, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)env->spec_smem);
   if (e != cudaSuccess) {
     mbe_destroy(env);
     return fail("mbe_create: cudaFuncSetAttribute(%zu B smem): %s", env->smem, cudaGetErrorString(e));
@@ -215,6 +281,16 @@ int mbe_bind(mbe_env* env, const mbe_buffers* b) {
   a.wp_cnt = b->wp_cnt;
   a.inj_k = b->inj_k;
   a.obs_bulk_ok = b->obs && (((uintptr_t)b->obs & 15) == 0);
+  if (!a.bs_per_env) {
+    // a shared layout is constant for the life of the binding: fold the coordinates into the
+    // kernel parameters (constant bank) for the specialised kernels
+    int16_t xy[2 * mbe::kMaxSlots];
+    MBE_CUDA(cudaMemcpy(xy, b->bs_xy, sizeof(int16_t) * 2 * a.B, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < a.B; ++i) {
+      a.slot[i].x = xy[2 * i];
+      a.slot[i].y = xy[2 * i + 1];
+    }
+  }
   env->bound = true;
   return 0;
 }
@@ -228,7 +304,9 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
   a.reset_mask = mask;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool gym = env->cfg.mode == MBE_MODE_GYM, ma = env->cfg.handler == MBE_HANDLER_MA;
-  if (!gym)
+  if (env->spec && op == mbe::OP_STEP && phases == MBE_PHASE_ALL)
+    env->spec<<<env->grid, mbe::kThreads, env->spec_smem, st>>>(a);
+  else if (!gym)
     mbe::step_kernel<0, 0><<<env->grid, mbe::kThreads, env->smem, st>>>(a);
   else if (!ma)
     mbe::step_kernel<1, 0><<<env->grid, mbe::kThreads, env->smem, st>>>(a);

@@ -9,16 +9,30 @@ namespace mbe {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxSlots = 32;
 
 enum Op : int { OP_STEP = 0, OP_RESET = 1, OP_OBSERVE = 2 };
 enum Purpose : unsigned { P_WAYPOINT = 0, P_INITPOS = 1, P_BSLAYOUT = 2 };
 
+// One BS class (include/mbe.h mbe_bs_class) as the kernels see it.
 struct ClassDev {
-  float l0_hi, l0_lo;  // log2 snr at d2 = 1, split hi+lo so the FP32 chain keeps ~2^-30 of it
+  float l0_hi, l0_lo;  // log2 snr at d2 = 1, split hi+lo (channel kernel keeps ~2^-30 of it)
   float k_hi, k_lo;    // slope per log2(d2)
   float l_zero;        // log2 snr at d2 == 0
   int d2max;           // connectable iff d2 <= d2max
-  const double* lut;   // rate_lut[d2], d2 in [0, d2max]
+  int stride;          // d2max + 1
+  int pad;
+  // lutn[(n-1)*stride + d2] = round(rate_lut[d2] / n, 2): Channel.datarate (channels.py:78-83)
+  // split over n UEs (schedules.py:20-22) and rounded like base.py:435, all in FP64
+  const double* lutn;
+};
+
+// One BS slot of a shared layout with its class folded in: every field becomes a constant-bank
+// operand once the specialised kernels unroll their loops over b.
+struct SlotDev {
+  int x, y, d2max, stride;
+  float k, l0, l_zero, pad;
+  const double* lutn;
 };
 
 struct StepArgs {
@@ -32,11 +46,13 @@ struct StepArgs {
   int ep_time, autoreset, reset_rng_episode, bs_per_env, bs_rand_min, bs_rand_max;
   unsigned seed_lo, seed_hi;
   double width, height, velocity;
+  float velocity_f, tie_eps;  // FP32 fast path of the movement and its fallback band
   int move_d2max;
   // utility: u = clip(util_c * log2(w2 + r), lo, hi); scaled = (u - lo) * util_scale - 1
   float util_c, util_w2, util_lo, util_hi, util_scale;
   int n_classes;
   ClassDev cls[8];
+  SlotDev slot[kMaxSlots];
   const uint8_t* bs_class;  // device [B] or nullptr
   // bound buffers (see include/mbe.h)
   uint32_t* pos;
@@ -81,8 +97,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 
 // x = int(u0 * W), y = int(u1 * H) with u = r * 2^-32 in FP64: the counter-based analogue of
 // int(rng.uniform(0, W)) (movement.py:45-46, 69-70).  Counter = (env gid, ue, t, purpose+4*salt).
-__device__ __forceinline__ void philox_point(const StepArgs& a, unsigned gid, unsigned ue, unsigned t,
-                                             unsigned purpose, unsigned salt, int& x, int& y) {
+__device__ __noinline__ void philox_point(const StepArgs& a, unsigned gid, unsigned ue, unsigned t,
+                                          unsigned purpose, unsigned salt, int& x, int& y) {
   uint4 r = philox4x32_10(make_uint4(gid, ue, t, purpose + 4u * salt), make_uint2(a.seed_lo, a.seed_hi));
   x = (int)((double)r.x * 0x1p-32 * a.width);
   y = (int)((double)r.y * 0x1p-32 * a.height);
@@ -99,15 +115,24 @@ __device__ __forceinline__ uint32_t pack_xy(int x, int y) {
 }
 __device__ __forceinline__ void unpack_xy(uint32_t p, int& x, int& y) {
   x = (int)(int16_t)(p & 0xffffu);
-  y = (int)(int16_t)(p >> 16);
+  y = (int)(p) >> 16;
 }
 
 // ---------------------------------------------------------------------------------------
-// RandomWaypointMovement.move once the waypoint exists (movement.py:49-62).  FP64 with the
-// reference's operation order: pos + (velocity * v) / norm(v), np.round (half-even), astype(int).
+// RandomWaypointMovement.move once the waypoint exists (movement.py:49-62).
+// Reference arithmetic (FP64): pos + (velocity * v) / norm(v), np.round (half-even), astype(int).
 // "norm <= velocity" is the integer test d2 <= move_d2max (host-folded, exact).
+// The step t = velocity*d/norm is first taken in FP32 (SFU rsqrt, |error| < 4e-7*velocity);
+// only when t lies within tie_eps of a rounding tie is the reference's FP64 chain replayed, so
+// the integer result is always the reference's.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ bool move_exact(const StepArgs& a, int& x, int& y, int wx, int wy) {
+__device__ __noinline__ void move_slow(const StepArgs& a, int& x, int& y, int dx, int dy, int d2) {
+  double norm = sqrt((double)d2);
+  x = (int)rint((double)x + (a.velocity * (double)dx) / norm);
+  y = (int)rint((double)y + (a.velocity * (double)dy) / norm);
+}
+
+__device__ __forceinline__ bool move_ue(const StepArgs& a, int& x, int& y, int wx, int wy) {
   int dx = wx - x, dy = wy - y;
   int d2 = dx * dx + dy * dy;
   if (d2 <= a.move_d2max) {
@@ -115,9 +140,16 @@ __device__ __forceinline__ bool move_exact(const StepArgs& a, int& x, int& y, in
     y = wy;
     return true;  // arrived: snap and pop the waypoint (movement.py:54-56)
   }
-  double norm = sqrt((double)d2);
-  x = (int)rint((double)x + (a.velocity * (double)dx) / norm);
-  y = (int)rint((double)y + (a.velocity * (double)dy) / norm);
+  float s = a.velocity_f * rsqrtf((float)d2);
+  float tx = (float)dx * s, ty = (float)dy * s;
+  float rx = rintf(tx), ry = rintf(ty);
+  float worst = fmaxf(fabsf(tx - rx), fabsf(ty - ry));  // distance to the nearest integer, <= 0.5
+  if (worst > 0.5f - a.tie_eps) {
+    move_slow(a, x, y, dx, dy, d2);
+  } else {
+    x += (int)rx;
+    y += (int)ry;
+  }
   return false;
 }
 
@@ -129,16 +161,19 @@ __device__ __forceinline__ float log2_snr(const ClassDev& c, int d2) {
   return fmaf(-c.k_lo, lg, l) + c.l0_lo;
 }
 
-// BoundedLogUtility.calculateUtility + scaleUtility (utilities.py:44-55)
-__device__ __forceinline__ float scaled_utility(const StepArgs& a, double rate) {
-  if (rate <= 0.0) return -1.0f;  // lower -> scaled -1
-  float u = a.util_c * log2f(a.util_w2 + (float)rate);
-  u = fminf(fmaxf(u, a.util_lo), a.util_hi);
-  return fmaf(u - a.util_lo, a.util_scale, -1.0f);
+// single-float form used for the observation ratios snr/max snr (error < 2e-6 relative)
+__device__ __forceinline__ float log2_snr_obs(float k, float l0, float l_zero, int d2) {
+  return d2 ? fmaf(-k, __log2f((float)d2), l0) : l_zero;
 }
 
-// round(rate, 2) of np.float64: rint(x*100)/100 (base.py:435)
-__device__ __forceinline__ double round2(double r) { return rint(r * 100.0) / 100.0; }
+// BoundedLogUtility.calculateUtility + scaleUtility (utilities.py:44-55); SFU lg2
+// (absolute error 2^-22 near 1, relative 2^-22 elsewhere).
+__device__ __forceinline__ float scaled_utility(const StepArgs& a, double rate) {
+  float u = a.util_c * __log2f(a.util_w2 + (float)rate);
+  u = fminf(fmaxf(u, a.util_lo), a.util_hi);
+  u = fmaf(u - a.util_lo, a.util_scale, -1.0f);
+  return (rate <= 0.0) ? -1.0f : u;  // rate <= 0 -> lower bound -> scaled -1
+}
 
 // Sum over the lanes of one env (contiguous segment of U lanes inside the warp), result
 // broadcast to every lane of the segment.  Fixed tree order => deterministic.
@@ -148,6 +183,71 @@ __device__ __forceinline__ float seg_sum(float v, int u, int U, int lane) {
     if (u + off < U) v += o;
   }
   return __shfl_sync(kFull, v, lane - u);
+}
+
+template <int U>
+__device__ __forceinline__ float seg_sum_c(float v, int u, int lane) {
+#pragma unroll
+  for (int off = 1; off < U; off <<= 1) {
+    float o = __shfl_down_sync(kFull, v, off);
+    if (u + off < U) v += o;
+  }
+  return __shfl_sync(kFull, v, lane - u);
+}
+
+// (Re)initialise one env: MComCore.reset + MComCustom.reset (base.py:172-209, custom.py:40-62).
+// `sel` is uniform over the lanes of an env; every lane of the warp must call (syncwarp inside).
+__device__ __noinline__ void reinit_env(const StepArgs& a, bool sel, unsigned gid, int u, size_t idx, int env,
+                                        uint32_t* sbs_env, int& epi, int& t_e, uint32_t& conn, int& x, int& y,
+                                        int& wx, int& wy, int& nb, bool& fresh) {
+  if (sel) {
+    epi += 1;
+    t_e = 0;
+    conn = 0;
+    wx = wy = -1;
+    philox_point(a, gid, (unsigned)u, 0u, P_INITPOS, a.reset_rng_episode ? 0u : (unsigned)epi, x, y);
+    if (a.inj_wp) a.wp_cnt[idx] = 0;
+    if (a.bs_rand_max > 0 && a.bs_per_env) {  // generate_base_stations (custom.py:68-77)
+      nb = philox_bs_count(a, gid, (unsigned)epi);
+      for (int b = u; b < a.B; b += a.U) {
+        int bx = 0, by = 0;
+        if (b < nb) philox_point(a, gid, (unsigned)b, 0u, P_BSLAYOUT, (unsigned)epi, bx, by);
+        uint32_t p = pack_xy(bx, by);
+        sbs_env[b] = p;
+        a.bs_xy[(size_t)env * a.B + b] = p;
+      }
+      if (u == 0 && a.nbs) a.nbs[env] = nb;
+    }
+    fresh = true;
+  }
+  __syncwarp();
+}
+
+// the observation block of a CTA leaves shared memory: one bulk async copy (TMA) when the
+// block is whole and aligned, else a predicated cooperative copy
+__device__ __forceinline__ void store_obs_block(const StepArgs& a, const float* sobs, int env_base, int tid,
+                                                bool whole) {
+  const int envs_here = min(a.epb, a.E - env_base);
+  const size_t words = (size_t)envs_here * a.U * a.F;
+  float* gdst = a.obs + (size_t)env_base * a.U * a.F;
+  if (whole && a.obs_bulk_ok && (words % 4 == 0)) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sobs);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr),
+                   "r"((uint32_t)(words * 4))
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  } else {
+    __syncthreads();
+    for (size_t i = tid; i < words; i += kThreads) {
+      int e = env_base + (int)(i / ((size_t)a.U * a.F));
+      if (whole || a.reset_mask[e] != 0) gdst[i] = sobs[i];
+    }
+  }
 }
 
 }  // namespace mbe

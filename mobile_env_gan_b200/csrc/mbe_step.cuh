@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
                      wx, wy);
       }
     }
-    if (move_exact(a, x, y, wx, wy)) wx = wy = -1;
+    if (move_ue(a, x, y, wx, wy)) wx = wy = -1;
   };
 
   // ---- PRE (FORK): nearest connectable BS, ResourceFair split, utility (base.py:236-258) ----
@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     double rate = 0.0;
     if (valid && best >= 0) {
       int n = __popc(peers);
-      rate = round2(a.cls[s.cls[best]].lut[bestd2] / (double)n);  // schedules.py:20-22, base.py:435
+      const ClassDev& c = a.cls[s.cls[best]];
+      rate = c.lutn[(size_t)(n - 1) * c.stride + bestd2];  // schedules.py:20-22, base.py:435
     }
     util = scaled_utility(a, rate);
     util_known = true;
@@ -205,7 +206,8 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
       unsigned m = __ballot_sync(kFull, bit) & segmask;
       if (bit) {  // allocateDataRate2User (base.py:421-435), bs-major accumulation (413-418)
         int n = __popc(m);
-        rate += round2(a.cls[s.cls[b]].lut[d2_to(b)] / (double)n);
+        const ClassDev& c = a.cls[s.cls[b]];
+        rate += c.lutn[(size_t)(n - 1) * c.stride + d2_to(b)];
       }
     }
     util = scaled_utility(a, rate);
@@ -246,30 +248,9 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     }
   };
 
-  // ---- (re)initialise an env: MComCore.reset + MComCustom.reset (base.py:172-209, custom.py:40-62)
   auto reinit = [&](bool sel) {
-    // sel is uniform over the lanes of an env
-    if (sel) {
-      epi += 1;
-      t_e = 0;
-      conn = 0;
-      wx = wy = -1;
-      philox_point(a, gid, (unsigned)u, 0u, P_INITPOS, a.reset_rng_episode ? 0u : (unsigned)epi, x, y);
-      if (a.inj_wp) a.wp_cnt[idx] = 0;
-      if (a.bs_rand_max > 0 && a.bs_per_env) {  // generate_base_stations (custom.py:68-77)
-        nb = philox_bs_count(a, gid, (unsigned)epi);
-        for (int b = u; b < B; b += U) {
-          int bx = 0, by = 0;
-          if (b < nb) philox_point(a, gid, (unsigned)b, 0u, P_BSLAYOUT, (unsigned)epi, bx, by);
-          uint32_t p = pack_xy(bx, by);
-          s.bs[env_in_blk * B + b] = p;
-          a.bs_xy[(size_t)env * B + b] = p;
-        }
-        if (u == 0 && a.nbs) a.nbs[env] = nb;
-      }
-      fresh = true;
-    }
-    __syncwarp();
+    reinit_env(a, sel, gid, u, idx, env, a.bs_per_env ? s.bs + (size_t)min(env_in_blk, a.epb - 1) * B : nullptr, epi,
+               t_e, conn, x, y, wx, wy, nb, fresh);
   };
 
   // ---- CLOCK: time += 1, departures, done (base.py:280-291, 407-409) ----
@@ -285,6 +266,8 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
   auto phase_post = [&]() {
     if (!GYM) return;
     if (!util_known && valid) util = a.utility[idx];
+    // when CLOCK ran in an earlier launch (split phases, mbe_observe) the clock tells
+    if (!(ph & 4)) done = valid && !fresh && (t_e >= a.ep_time);
     const bool is_fresh = fresh || (t_e == 0);
     if (MA) {
       // warp-collective: every lane takes part as soon as one env of the warp needs fresh
@@ -303,7 +286,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     for (int b = 0; b < nb; ++b) {
       const ClassDev& c = a.cls[s.cls[b]];
       int d2 = d2_to(b);
-      float l = log2_snr(c, d2);
+      float l = log2_snr_obs(c.k_hi, c.l0_hi, c.l_zero, d2);
       row[B + b] = l;
       lmax = fmaxf(lmax, l);
       if (d2 <= c.d2max) elig |= 1u << b;
@@ -368,30 +351,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
   }
 
   // ---- observation block leaves shared memory ----
-  if (GYM && (ph & 8)) {
-    const int envs_here = min(a.epb, a.E - env_base);
-    const size_t words = (size_t)envs_here * U * F;
-    float* gdst = a.obs + (size_t)env_base * U * F;
-    const bool whole = (op != OP_RESET || a.reset_mask == nullptr);
-    if (whole && a.obs_bulk_ok && (words % 4 == 0)) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
-      if (tid == 0) {
-        uint32_t saddr = (uint32_t)__cvta_generic_to_shared(s.obs);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr),
-                     "r"((uint32_t)(words * 4))
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      }
-    } else {
-      __syncthreads();
-      for (size_t i = tid; i < words; i += kThreads) {
-        int e = env_base + (int)(i / ((size_t)U * F));
-        if (whole || a.reset_mask[e] != 0) gdst[i] = s.obs[i];
-      }
-    }
-  }
+  if (GYM && (ph & 8)) store_obs_block(a, s.obs, env_base, tid, op != OP_RESET || a.reset_mask == nullptr);
 }
 
 // Channel.calculateSNR for every pair (channels.py:24-27): thread per (env, ue), BS table in

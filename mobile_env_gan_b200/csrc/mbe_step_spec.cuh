@@ -1,0 +1,321 @@
+// Specialised fused step kernels: U (UEs) and B (BS slots) are template constants, so every
+// loop over b unrolls, BS coordinates / channel constants of a shared layout are constant-bank
+// operands (no shared-memory table, no unpacking) and the per-pair values stay in registers.
+// Same warp-segment mapping and the same arithmetic helpers as the generic kernel
+// (mbe_step.cuh), which remains the path for reset / observe / split phases and for shapes
+// without an instantiation.  Only the whole fused step (OP_STEP, all phases) runs here.
+#pragma once
+#include "mbe_device.cuh"
+
+namespace mbe {
+
+template <int HANDLER, int U, int B, bool PER_ENV>
+__host__ __device__ constexpr size_t spec_smem_bytes(bool gym) {
+  constexpr int EPB = (32 / U) * kWarpsPerBlock;
+  constexpr int F = (HANDLER == 1 ? 4 : 2) * B + 1;
+  size_t n = gym ? (size_t)EPB * U * F * 4 : 0;
+  n = (n + 15) & ~(size_t)15;
+  if (PER_ENV) n += (size_t)EPB * B * 4;
+  if (gym && HANDLER == 1) n += (size_t)EPB * B * 8;
+  return (n + 15) & ~(size_t)15;
+}
+
+template <int MODE, int HANDLER, int U, int B, bool PER_ENV>
+__global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr bool GYM = (MODE == 1);
+  constexpr bool MA = (HANDLER == 1);
+  constexpr int EPW = 32 / U;
+  constexpr int EPB = EPW * kWarpsPerBlock;
+  constexpr int F = GYM ? ((MA ? 4 : 2) * B + 1) : 0;
+  constexpr unsigned SEG = (U == 32) ? kFull : ((1u << U) - 1u);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  float* s_obs = reinterpret_cast<float*>(smem_raw);
+  constexpr size_t OBS_BYTES = (((size_t)(GYM ? EPB * U * F * 4 : 0)) + 15) & ~(size_t)15;
+  uint32_t* s_bs = reinterpret_cast<uint32_t*>(smem_raw + OBS_BYTES);
+  constexpr size_t BS_BYTES = PER_ENV ? (size_t)EPB * B * 4 : 0;
+  float* s_bsu = reinterpret_cast<float*>(smem_raw + OBS_BYTES + BS_BYTES);
+  int* s_bsn = reinterpret_cast<int*>(smem_raw + OBS_BYTES + BS_BYTES + (size_t)EPB * B * 4);
+
+  const int env_base = blockIdx.x * EPB;
+  if (PER_ENV) {
+    const int n = min(EPB, a.E - env_base) * B;
+    const uint32_t* g = a.bs_xy + (size_t)env_base * B;
+    for (int i = tid; i < n; i += kThreads) s_bs[i] = g[i];
+    __syncthreads();
+  }
+
+  int seg = lane / U;
+  int u = lane - seg * U;
+  if (seg >= EPW) {
+    seg = EPW;
+    u = lane - EPW * U;
+  }
+  const int env_in_blk = warp * EPW + seg;
+  const int env = env_base + env_in_blk;
+  const bool valid = (seg < EPW) && (env < a.E);
+  const unsigned segmask = valid ? (SEG << (seg * U)) : 0u;
+  const size_t idx = (size_t)env * U + u;
+  const unsigned gid = a.env_offset + (unsigned)env;
+  uint32_t* bs_env = PER_ENV ? s_bs + (size_t)min(env_in_blk, EPB - 1) * B : nullptr;
+
+  // ---- load state (all loads issued before any use) ----
+  int x = 0, y = 0, wx = -1, wy = -1, t_e = 0, epi = 0, nb = B, act = 0;
+  uint32_t conn = 0;
+  if (valid) {
+    uint32_t p = a.pos[idx], w = a.wp[idx];
+    if (GYM) {
+      conn = a.conn[idx];
+      act = a.actions[idx];
+    }
+    t_e = a.t[env];
+    epi = a.episode[env];
+    if (PER_ENV && a.nbs) nb = a.nbs[env];
+    unpack_xy(p, x, y);
+    unpack_xy(w, wx, wy);
+  }
+  const uint32_t pos_in = pack_xy(x, y), wp_in = pack_xy(wx, wy), conn_in = conn;
+  bool done = false, fresh = false;
+  float util = -1.0f;
+
+  // geometry / channel constants of BS slot b
+  auto bs_xy_of = [&](int b, int& bx, int& by) {
+    if (PER_ENV) {
+      unpack_xy(bs_env[b], bx, by);
+    } else {
+      bx = a.slot[b].x;
+      by = a.slot[b].y;
+    }
+  };
+  auto d2_to = [&](int b) {
+    int bx, by;
+    bs_xy_of(b, bx, by);
+    int dx = x - bx, dy = y - by;
+    return dx * dx + dy * dy;
+  };
+  auto slot_of = [&](int b) -> const SlotDev& { return a.slot[PER_ENV ? 0 : b]; };
+
+  auto phase_move = [&]() {
+    if (!valid) return;
+    if (wx < 0) {  // no waypoint: draw one (movement.py:44-47)
+      if (a.inj_wp) {
+        int k = a.wp_cnt[idx];
+        unpack_xy(a.inj_wp[idx * a.inj_k + min(k, a.inj_k - 1)], wx, wy);
+        a.wp_cnt[idx] = k + 1;
+      } else {
+        philox_point(a, gid, (unsigned)u, (unsigned)t_e, P_WAYPOINT, a.reset_rng_episode ? 0u : (unsigned)epi,
+                     wx, wy);
+      }
+    }
+    if (move_ue(a, x, y, wx, wy)) wx = wy = -1;
+  };
+
+  auto phase_clock = [&]() {
+    t_e += 1;
+    done = valid && (t_e >= a.ep_time);
+    if (done) conn = 0;  // everyone leaves at ep_time (arrival.py:32-36, base.py:283-285)
+    if (valid && u == 0) a.done[env] = done ? 1 : 0;
+    if (__any_sync(kFull, done && a.autoreset))
+      reinit_env(a, done && a.autoreset, gid, u, idx, env, bs_env, epi, t_e, conn, x, y, wx, wy, nb, fresh);
+  };
+
+  if (!GYM) {
+    // ================= FORK: move -> associate -> split -> utility (base.py:230-296) =================
+    phase_move();
+    int best = -1, bestd2 = 0x7fffffff;
+    if (valid) {
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        int d2 = d2_to(b);
+        bool ok = (d2 <= slot_of(b).d2max) && (d2 < bestd2);  // strict <: first minimum (base.py:240)
+        if (PER_ENV) ok = ok && (b < nb);
+        if (ok) {
+          best = b;
+          bestd2 = d2;
+        }
+      }
+    }
+    const bool has = valid && best >= 0;
+    unsigned peers = __match_any_sync(kFull, has ? (seg * 64 + best) : (0x10000 + lane));
+    double rate = 0.0;
+    if (has) {
+      const SlotDev& c = slot_of(best);
+      rate = c.lutn[(size_t)(__popc(peers) - 1) * c.stride + bestd2];  // schedules.py:20-22, base.py:435
+    }
+    util = scaled_utility(a, rate);
+    if (valid) {
+      a.assoc[idx] = best;
+      if (a.rate) a.rate[idx] = rate;
+      a.utility[idx] = util;
+    }
+    if (a.metrics) {
+      unsigned cm = __ballot_sync(kFull, has) & segmask;
+      float usum = seg_sum_c<U>(valid ? util : 0.0f, u, lane);
+      float rsum = seg_sum_c<U>((float)rate, u, lane);
+      if (valid && u == 0) {
+        int nc = __popc(cm);
+        reinterpret_cast<float4*>(a.metrics)[env] =
+            make_float4((float)nc, (float)nc, usum / (float)U, nc ? rsum / (float)nc : 0.0f);
+      }
+    }
+    if (valid && a.dbg_snr) {
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        const SlotDev& c = slot_of(b);
+        a.dbg_snr[idx * B + b] = (b < nb) ? exp2f(log2_snr_obs(c.k, c.l0, c.l_zero, d2_to(b))) : 0.0f;
+      }
+    }
+    phase_clock();
+  } else {
+    // ================= GYM: actions -> split -> utility -> reward -> move -> obs =================
+    uint32_t elig = 0;
+    int d2pre[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      d2pre[b] = d2_to(b);
+      bool ok = d2pre[b] <= slot_of(b).d2max;  // check_connectivity (base.py:212-214)
+      if (PER_ENV) ok = ok && (b < nb);
+      elig |= ok ? (1u << b) : 0u;
+    }
+    if (!valid) elig = 0;
+    conn &= elig;  // update_connections (base.py:221-227)
+    if (act > 0 && act <= nb) {  // NOOP_ACTION = 0 (base.py:29)
+      uint32_t bit = 1u << (act - 1);
+      conn = (conn & bit) ? (conn & ~bit) : (conn | (elig & bit));
+    }
+    double rate = 0.0;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      bool bit = (conn >> b) & 1u;
+      unsigned m = __ballot_sync(kFull, bit) & segmask;
+      if (bit) {  // allocateDataRate2User (base.py:421-435), bs-major accumulation (413-418)
+        const SlotDev& c = slot_of(b);
+        rate += c.lutn[(size_t)(__popc(m) - 1) * c.stride + d2pre[b]];
+      }
+    }
+    util = scaled_utility(a, rate);
+    float usum = seg_sum_c<U>(valid ? util : 0.0f, u, lane);
+    if (valid) {
+      if (a.rate) a.rate[idx] = rate;
+      a.utility[idx] = util;
+    }
+    if (MA) {
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        bool bit = valid && ((conn >> b) & 1u);
+        unsigned m = __ballot_sync(kFull, bit) & segmask;
+        float sum = seg_sum_c<U>(bit ? util : 0.0f, u, lane);
+        if (valid && u == 0) {
+          int n = __popc(m);
+          s_bsn[env_in_blk * B + b] = n;
+          s_bsu[env_in_blk * B + b] = n ? sum / (float)n : -1.0f;
+        }
+      }
+      __syncwarp();
+      if (valid) {
+        float nu = 0.0f;
+        int ncnt = 0;
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+          if ((elig >> b) & 1u) {  // available_connections (base.py:216-218)
+            nu += s_bsu[env_in_blk * B + b];
+            ncnt += s_bsn[env_in_blk * B + b];
+          }
+        a.reward[idx] = (nu + util) / (float)(ncnt + 1);
+      }
+    } else if (valid && u == 0) {
+      a.reward[env] = usum / (float)U;  // mean utility (metrics.py:25-28)
+    }
+    if (a.metrics) {
+      unsigned cm = __ballot_sync(kFull, valid && conn != 0) & segmask;
+      float csum = seg_sum_c<U>((float)__popc(conn), u, lane);
+      float rsum = seg_sum_c<U>((float)rate, u, lane);
+      if (valid && u == 0) {
+        int nc = __popc(cm);
+        reinterpret_cast<float4*>(a.metrics)[env] =
+            make_float4(csum, (float)nc, usum / (float)U, nc ? rsum / (float)nc : 0.0f);
+      }
+    }
+    if (valid && a.dbg_snr) {
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        const SlotDev& c = slot_of(b);
+        a.dbg_snr[idx * B + b] = (b < nb) ? exp2f(log2_snr_obs(c.k, c.l0, c.l_zero, d2pre[b])) : 0.0f;
+      }
+    }
+
+    phase_move();
+    phase_clock();
+
+    // ---- observation of the new state ----
+    if (MA) {
+      // statistics change only for envs that ended (connections dropped / fresh episode)
+      if (__any_sync(kFull, done)) {
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+          if (done && u == 0) {
+            s_bsn[env_in_blk * B + b] = 0;
+            s_bsu[env_in_blk * B + b] = -1.0f;
+          }
+        __syncwarp();
+      }
+    }
+    if (valid) {
+      float* row = s_obs + ((size_t)env_in_blk * U + u) * F;
+      if (done && !fresh) {  // inactive UEs observe zeros
+#pragma unroll
+        for (int f = 0; f < F; ++f) row[f] = 0.0f;
+      } else {
+        float l[B];
+        float lmax = -INFINITY;
+        uint32_t elig2 = 0;
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          const SlotDev& c = slot_of(b);
+          int d2 = d2_to(b);
+          l[b] = log2_snr_obs(c.k, c.l0, c.l_zero, d2);
+          bool live = !PER_ENV || (b < nb);
+          if (!live) l[b] = -INFINITY;
+          lmax = fmaxf(lmax, l[b]);
+          if (live && d2 <= c.d2max) elig2 |= 1u << b;
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          row[b] = ((conn >> b) & 1u) ? 1.0f : 0.0f;
+          row[B + b] = exp2f(l[b] - lmax);  // snr / max snr
+        }
+        row[2 * B] = fresh ? -1.0f : util;
+        if (MA) {
+          float cnt[B];
+          float tot = 0.0f;
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            bool ok = (elig2 >> b) & 1u;
+            cnt[b] = ok ? (float)s_bsn[env_in_blk * B + b] : 0.0f;
+            row[2 * B + 1 + b] = ok ? s_bsu[env_in_blk * B + b] : -1.0f;
+            tot += cnt[b];
+          }
+          float inv = 1.0f / fmaxf(1.0f, tot);
+#pragma unroll
+          for (int b = 0; b < B; ++b) row[3 * B + 1 + b] = cnt[b] * inv;
+        }
+      }
+    }
+  }
+
+  // ---- store state (only what changed) ----
+  if (valid) {
+    uint32_t p = pack_xy(x, y), w = pack_xy(wx, wy);
+    if (p != pos_in) a.pos[idx] = p;
+    if (w != wp_in) a.wp[idx] = w;
+    if (GYM && conn != conn_in) a.conn[idx] = conn;
+    if (u == 0) {
+      a.t[env] = t_e;
+      if (fresh) a.episode[env] = epi;
+    }
+  }
+  if (GYM) store_obs_block(a, s_obs, env_base, tid, true);
+}
+
+}  // namespace mbe
