@@ -148,6 +148,7 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   a.util_lo = (float)cfg->util_lower;
   a.util_hi = (float)cfg->util_upper;
   a.util_scale = (float)(2.0 / (cfg->util_upper - cfg->util_lower));
+  a.inv_U = 1.0f / (float)a.U;
   a.n_classes = cfg->num_classes;
   for (int c = 0; c < cfg->num_classes; ++c) {
     const mbe_bs_class& h = cfg->classes[c];
@@ -209,7 +210,11 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     sl.pad = 0.0f;
     sl.lutn = d.lutn;
   }
-  if (!(cfg->flags & MBE_FLAG_GENERIC_KERNEL)) {
+  // the specialised kernels assume one BS class and squared distances exact in FP32
+  const bool spec_ok = cfg->num_classes == 1 &&
+                       std::floor(cfg->width) * std::floor(cfg->width) + std::floor(cfg->height) * std::floor(cfg->height) <
+                           16777216.0;
+  if (spec_ok && !(cfg->flags & MBE_FLAG_GENERIC_KERNEL)) {
     for (const SpecEntry& sp : kSpecs)
       if (sp.mode == cfg->mode && (sp.handler == cfg->handler || !gym) && sp.U == a.U && sp.B == a.B &&
           sp.per_env == a.bs_per_env) {

@@ -50,6 +50,7 @@ struct StepArgs {
   int move_d2max;
   // utility: u = clip(util_c * log2(w2 + r), lo, hi); scaled = (u - lo) * util_scale - 1
   float util_c, util_w2, util_lo, util_hi, util_scale;
+  float inv_U;  // 1/U for the per-env means
   int n_classes;
   ClassDev cls[8];
   SlotDev slot[kMaxSlots];
@@ -97,7 +98,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 
 // x = int(u0 * W), y = int(u1 * H) with u = r * 2^-32 in FP64: the counter-based analogue of
 // int(rng.uniform(0, W)) (movement.py:45-46, 69-70).  Counter = (env gid, ue, t, purpose+4*salt).
-__device__ __noinline__ void philox_point(const StepArgs& a, unsigned gid, unsigned ue, unsigned t,
+__device__ __forceinline__ void philox_point(const StepArgs& a, unsigned gid, unsigned ue, unsigned t,
                                           unsigned purpose, unsigned salt, int& x, int& y) {
   uint4 r = philox4x32_10(make_uint4(gid, ue, t, purpose + 4u * salt), make_uint2(a.seed_lo, a.seed_hi));
   x = (int)((double)r.x * 0x1p-32 * a.width);
@@ -108,6 +109,18 @@ __device__ __forceinline__ int philox_bs_count(const StepArgs& a, unsigned gid, 
   uint4 r = philox4x32_10(make_uint4(gid, 0xFFFFu, 0xFFFFu, P_BSLAYOUT + 4u * salt),
                           make_uint2(a.seed_lo, a.seed_hi));
   return a.bs_rand_min + (int)((double)r.x * 0x1p-32 * (double)(a.bs_rand_max - a.bs_rand_min + 1));
+}
+
+// raw SFU ops (flush-to-zero: one MUFU each, no denormal fix-up code around them)
+__device__ __forceinline__ float lg2_sfu(float v) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float ex2_sfu(float v) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
 }
 
 __device__ __forceinline__ uint32_t pack_xy(int x, int y) {
@@ -126,7 +139,7 @@ __device__ __forceinline__ void unpack_xy(uint32_t p, int& x, int& y) {
 // only when t lies within tie_eps of a rounding tie is the reference's FP64 chain replayed, so
 // the integer result is always the reference's.
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void move_slow(const StepArgs& a, int& x, int& y, int dx, int dy, int d2) {
+__device__ __forceinline__ void move_slow(const StepArgs& a, int& x, int& y, int dx, int dy, int d2) {
   double norm = sqrt((double)d2);
   x = (int)rint((double)x + (a.velocity * (double)dx) / norm);
   y = (int)rint((double)y + (a.velocity * (double)dy) / norm);
@@ -156,24 +169,31 @@ __device__ __forceinline__ bool move_ue(const StepArgs& a, int& x, int& y, int w
 // log2 of the SNR (channels.py:24-27 + 132-146 folded): l0 - k*log2(d2); SFU lg2 on FP32.
 __device__ __forceinline__ float log2_snr(const ClassDev& c, int d2) {
   if (d2 == 0) return c.l_zero;
-  float lg = __log2f((float)d2);
+  float lg = lg2_sfu((float)d2);
   float l = fmaf(-c.k_hi, lg, c.l0_hi);
   return fmaf(-c.k_lo, lg, l) + c.l0_lo;
 }
 
 // single-float form used for the observation ratios snr/max snr (error < 2e-6 relative)
 __device__ __forceinline__ float log2_snr_obs(float k, float l0, float l_zero, int d2) {
-  return d2 ? fmaf(-k, __log2f((float)d2), l0) : l_zero;
+  return d2 ? fmaf(-k, lg2_sfu((float)d2), l0) : l_zero;
+}
+// same with the squared distance already in FP32 (exact for d2 < 2^24)
+__device__ __forceinline__ float log2_snr_obs_f(float k, float l0, float l_zero, float d2f) {
+  return (d2f > 0.0f) ? fmaf(-k, lg2_sfu(d2f), l0) : l_zero;
 }
 
 // BoundedLogUtility.calculateUtility + scaleUtility (utilities.py:44-55); SFU lg2
 // (absolute error 2^-22 near 1, relative 2^-22 elsewhere).
 __device__ __forceinline__ float scaled_utility(const StepArgs& a, double rate) {
-  float u = a.util_c * __log2f(a.util_w2 + (float)rate);
+  float u = a.util_c * lg2_sfu(a.util_w2 + (float)rate);
   u = fminf(fmaxf(u, a.util_lo), a.util_hi);
   u = fmaf(u - a.util_lo, a.util_scale, -1.0f);
   return (rate <= 0.0) ? -1.0f : u;  // rate <= 0 -> lower bound -> scaled -1
 }
+
+// mean over the connected UEs (metrics.py:18-21): 0 when nobody is connected
+__device__ __forceinline__ float mean_or_zero(float sum, float n) { return n > 0.0f ? __fdividef(sum, n) : 0.0f; }
 
 // Sum over the lanes of one env (contiguous segment of U lanes inside the warp), result
 // broadcast to every lane of the segment.  Fixed tree order => deterministic.
@@ -197,7 +217,7 @@ __device__ __forceinline__ float seg_sum_c(float v, int u, int lane) {
 
 // (Re)initialise one env: MComCore.reset + MComCustom.reset (base.py:172-209, custom.py:40-62).
 // `sel` is uniform over the lanes of an env; every lane of the warp must call (syncwarp inside).
-__device__ __noinline__ void reinit_env(const StepArgs& a, bool sel, unsigned gid, int u, size_t idx, int env,
+__device__ __forceinline__ void reinit_env(const StepArgs& a, bool sel, unsigned gid, int u, size_t idx, int env,
                                         uint32_t* sbs_env, int& epi, int& t_e, uint32_t& conn, int& x, int& y,
                                         int& wx, int& wy, int& nb, bool& fresh) {
   if (sel) {

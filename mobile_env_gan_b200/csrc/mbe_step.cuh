@@ -175,13 +175,12 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
       if (a.rate) a.rate[idx] = rate;
       a.utility[idx] = util;
       if (a.metrics && u == 0) {
-        int nc = __popc(cm);
-        float4 m = make_float4((float)nc, (float)nc, usum / (float)U, nc ? rsum / (float)nc : 0.0f);
-        reinterpret_cast<float4*>(a.metrics)[env] = m;
+        float nc = (float)__popc(cm);
+        reinterpret_cast<float4*>(a.metrics)[env] = make_float4(nc, nc, usum * a.inv_U, mean_or_zero(rsum, nc));
       }
       if (a.dbg_snr) {
         for (int b = 0; b < B; ++b)
-          a.dbg_snr[idx * B + b] = (b < nb) ? exp2f(log2_snr(a.cls[s.cls[b]], d2_to(b))) : 0.0f;
+          a.dbg_snr[idx * B + b] = (b < nb) ? ex2_sfu(log2_snr(a.cls[s.cls[b]], d2_to(b))) : 0.0f;
       }
     }
   };
@@ -230,21 +229,20 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
         a.reward[idx] = (nu + util) / (float)(ncnt + 1);
       }
     } else if (valid && u == 0) {
-      a.reward[env] = usum / (float)U;  // mean utility (metrics.py:25-28)
+      a.reward[env] = usum * a.inv_U;  // mean utility (metrics.py:25-28)
     }
     if (a.metrics) {
       unsigned cm = __ballot_sync(kFull, valid && conn != 0) & segmask;
       float csum = seg_sum((float)__popc(conn), u, U, lane);
       float rsum = seg_sum((float)rate, u, U, lane);
       if (valid && u == 0) {
-        int nc = __popc(cm);
-        reinterpret_cast<float4*>(a.metrics)[env] =
-            make_float4(csum, (float)nc, usum / (float)U, nc ? rsum / (float)nc : 0.0f);
+        float nc = (float)__popc(cm);
+        reinterpret_cast<float4*>(a.metrics)[env] = make_float4(csum, nc, usum * a.inv_U, mean_or_zero(rsum, nc));
       }
     }
     if (valid && a.dbg_snr) {
       for (int b = 0; b < B; ++b)
-        a.dbg_snr[idx * B + b] = (b < nb) ? exp2f(log2_snr(a.cls[s.cls[b]], d2_to(b))) : 0.0f;
+        a.dbg_snr[idx * B + b] = (b < nb) ? ex2_sfu(log2_snr(a.cls[s.cls[b]], d2_to(b))) : 0.0f;
     }
   };
 
@@ -293,7 +291,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     }
     for (int b = 0; b < B; ++b) {
       row[b] = ((conn >> b) & 1u) ? 1.0f : 0.0f;
-      row[B + b] = (b < nb) ? exp2f(row[B + b] - lmax) : 0.0f;  // snr / max snr
+      row[B + b] = (b < nb) ? ex2_sfu(row[B + b] - lmax) : 0.0f;  // snr / max snr
     }
     row[2 * B] = is_fresh ? -1.0f : util;
     if (MA) {
@@ -390,7 +388,7 @@ __global__ void __launch_bounds__(kThreads) channel_kernel(const __grid_constant
       unpack_xy(tab[b], bx, by);
       int dx = x - bx, dy = y - by, d2 = dx * dx + dy * dy;
       const ClassDev& c = a.cls[scls[b]];
-      snr = exp2f(log2_snr(c, d2));
+      snr = ex2_sfu(log2_snr(c, d2));
       if (d2 <= c.d2max) elig |= 1u << b;
     }
     if (out_snr) out_snr[idx * B + b] = snr;

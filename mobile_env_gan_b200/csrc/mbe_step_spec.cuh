@@ -1,9 +1,11 @@
 // Specialised fused step kernels: U (UEs) and B (BS slots) are template constants, so every
-// loop over b unrolls, BS coordinates / channel constants of a shared layout are constant-bank
-// operands (no shared-memory table, no unpacking) and the per-pair values stay in registers.
+// loop over b unrolls, BS coordinates of a shared layout are constant-bank operands (no
+// shared-memory table, no unpacking) and the per-pair values stay in registers.
 // Same warp-segment mapping and the same arithmetic helpers as the generic kernel
 // (mbe_step.cuh), which remains the path for reset / observe / split phases and for shapes
 // without an instantiation.  Only the whole fused step (OP_STEP, all phases) runs here.
+// Preconditions checked by the dispatcher (mbe.cu): one BS class, width^2+height^2 < 2^24
+// (squared distances are exact in FP32).
 #pragma once
 #include "mbe_device.cuh"
 
@@ -56,30 +58,37 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
   const int env = env_base + env_in_blk;
   const bool valid = (seg < EPW) && (env < a.E);
   const unsigned segmask = valid ? (SEG << (seg * U)) : 0u;
-  const size_t idx = (size_t)env * U + u;
+  // idle lanes (32 - EPW*U per warp, and the tail of the last block) run the same code on a
+  // clamped index and only their stores are predicated off
+  const int env_ld = valid ? env : 0;
+  const unsigned idx = (unsigned)env_ld * U + (valid ? u : 0);
   const unsigned gid = a.env_offset + (unsigned)env;
   uint32_t* bs_env = PER_ENV ? s_bs + (size_t)min(env_in_blk, EPB - 1) * B : nullptr;
+  const SlotDev& C0 = a.slot[0];  // the single BS class
 
   // ---- load state (all loads issued before any use) ----
-  int x = 0, y = 0, wx = -1, wy = -1, t_e = 0, epi = 0, nb = B, act = 0;
+  const uint32_t pos_in = a.pos[idx], wp_in = a.wp[idx];
   uint32_t conn = 0;
-  if (valid) {
-    uint32_t p = a.pos[idx], w = a.wp[idx];
-    if (GYM) {
-      conn = a.conn[idx];
-      act = a.actions[idx];
-    }
-    t_e = a.t[env];
-    epi = a.episode[env];
-    if (PER_ENV && a.nbs) nb = a.nbs[env];
-    unpack_xy(p, x, y);
-    unpack_xy(w, wx, wy);
+  int act = 0;
+  if (GYM) {
+    conn = a.conn[idx];
+    act = a.actions[idx];
   }
-  const uint32_t pos_in = pack_xy(x, y), wp_in = pack_xy(wx, wy), conn_in = conn;
+  int t_e = a.t[env_ld];
+  int epi = a.episode[env_ld];
+  int nb = B;
+  if (PER_ENV && a.nbs) nb = a.nbs[env_ld];
+  int x, y, wx, wy;
+  unpack_xy(pos_in, x, y);
+  unpack_xy(wp_in, wx, wy);
+  if (!valid) {
+    conn = 0;
+    act = 0;
+  }
+  const uint32_t conn_in = conn;
   bool done = false, fresh = false;
   float util = -1.0f;
 
-  // geometry / channel constants of BS slot b
   auto bs_xy_of = [&](int b, int& bx, int& by) {
     if (PER_ENV) {
       unpack_xy(bs_env[b], bx, by);
@@ -94,15 +103,17 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
     int dx = x - bx, dy = y - by;
     return dx * dx + dy * dy;
   };
-  auto slot_of = [&](int b) -> const SlotDev& { return a.slot[PER_ENV ? 0 : b]; };
 
   auto phase_move = [&]() {
-    if (!valid) return;
     if (wx < 0) {  // no waypoint: draw one (movement.py:44-47)
       if (a.inj_wp) {
-        int k = a.wp_cnt[idx];
-        unpack_xy(a.inj_wp[idx * a.inj_k + min(k, a.inj_k - 1)], wx, wy);
-        a.wp_cnt[idx] = k + 1;
+        if (valid) {
+          int k = a.wp_cnt[idx];
+          unpack_xy(a.inj_wp[(size_t)idx * a.inj_k + min(k, a.inj_k - 1)], wx, wy);
+          a.wp_cnt[idx] = k + 1;
+        } else {
+          wx = wy = 0;
+        }
       } else {
         philox_point(a, gid, (unsigned)u, (unsigned)t_e, P_WAYPOINT, a.reset_rng_episode ? 0u : (unsigned)epi,
                      wx, wy);
@@ -124,25 +135,20 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
     // ================= FORK: move -> associate -> split -> utility (base.py:230-296) =================
     phase_move();
     int best = -1, bestd2 = 0x7fffffff;
-    if (valid) {
 #pragma unroll
-      for (int b = 0; b < B; ++b) {
-        int d2 = d2_to(b);
-        bool ok = (d2 <= slot_of(b).d2max) && (d2 < bestd2);  // strict <: first minimum (base.py:240)
-        if (PER_ENV) ok = ok && (b < nb);
-        if (ok) {
-          best = b;
-          bestd2 = d2;
-        }
+    for (int b = 0; b < B; ++b) {
+      int d2 = d2_to(b);
+      bool ok = (d2 <= C0.d2max) && (d2 < bestd2);  // strict <: first minimum wins (base.py:240)
+      if (PER_ENV) ok = ok && (b < nb);
+      if (ok) {
+        best = b;
+        bestd2 = d2;
       }
     }
     const bool has = valid && best >= 0;
     unsigned peers = __match_any_sync(kFull, has ? (seg * 64 + best) : (0x10000 + lane));
     double rate = 0.0;
-    if (has) {
-      const SlotDev& c = slot_of(best);
-      rate = c.lutn[(size_t)(__popc(peers) - 1) * c.stride + bestd2];  // schedules.py:20-22, base.py:435
-    }
+    if (has) rate = C0.lutn[(unsigned)(__popc(peers) - 1) * (unsigned)C0.stride + (unsigned)bestd2];
     util = scaled_utility(a, rate);
     if (valid) {
       a.assoc[idx] = best;
@@ -154,17 +160,14 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
       float usum = seg_sum_c<U>(valid ? util : 0.0f, u, lane);
       float rsum = seg_sum_c<U>((float)rate, u, lane);
       if (valid && u == 0) {
-        int nc = __popc(cm);
-        reinterpret_cast<float4*>(a.metrics)[env] =
-            make_float4((float)nc, (float)nc, usum / (float)U, nc ? rsum / (float)nc : 0.0f);
+        float nc = (float)__popc(cm);
+        reinterpret_cast<float4*>(a.metrics)[env] = make_float4(nc, nc, usum * a.inv_U, mean_or_zero(rsum, nc));
       }
     }
     if (valid && a.dbg_snr) {
 #pragma unroll
-      for (int b = 0; b < B; ++b) {
-        const SlotDev& c = slot_of(b);
-        a.dbg_snr[idx * B + b] = (b < nb) ? exp2f(log2_snr_obs(c.k, c.l0, c.l_zero, d2_to(b))) : 0.0f;
-      }
+      for (int b = 0; b < B; ++b)
+        a.dbg_snr[(size_t)idx * B + b] = (b < nb) ? ex2_sfu(log2_snr_obs(C0.k, C0.l0, C0.l_zero, d2_to(b))) : 0.0f;
     }
     phase_clock();
   } else {
@@ -174,11 +177,10 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
 #pragma unroll
     for (int b = 0; b < B; ++b) {
       d2pre[b] = d2_to(b);
-      bool ok = d2pre[b] <= slot_of(b).d2max;  // check_connectivity (base.py:212-214)
+      bool ok = d2pre[b] <= C0.d2max;  // check_connectivity (base.py:212-214)
       if (PER_ENV) ok = ok && (b < nb);
       elig |= ok ? (1u << b) : 0u;
     }
-    if (!valid) elig = 0;
     conn &= elig;  // update_connections (base.py:221-227)
     if (act > 0 && act <= nb) {  // NOOP_ACTION = 0 (base.py:29)
       uint32_t bit = 1u << (act - 1);
@@ -189,10 +191,8 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
     for (int b = 0; b < B; ++b) {
       bool bit = (conn >> b) & 1u;
       unsigned m = __ballot_sync(kFull, bit) & segmask;
-      if (bit) {  // allocateDataRate2User (base.py:421-435), bs-major accumulation (413-418)
-        const SlotDev& c = slot_of(b);
-        rate += c.lutn[(size_t)(__popc(m) - 1) * c.stride + d2pre[b]];
-      }
+      if (bit)  // allocateDataRate2User (base.py:421-435), bs-major accumulation (413-418)
+        rate += C0.lutn[(unsigned)(__popc(m) - 1) * (unsigned)C0.stride + (unsigned)d2pre[b]];
     }
     util = scaled_utility(a, rate);
     float usum = seg_sum_c<U>(valid ? util : 0.0f, u, lane);
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
     if (MA) {
 #pragma unroll
       for (int b = 0; b < B; ++b) {
-        bool bit = valid && ((conn >> b) & 1u);
+        bool bit = (conn >> b) & 1u;
         unsigned m = __ballot_sync(kFull, bit) & segmask;
         float sum = seg_sum_c<U>(bit ? util : 0.0f, u, lane);
         if (valid && u == 0) {
@@ -225,24 +225,21 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
         a.reward[idx] = (nu + util) / (float)(ncnt + 1);
       }
     } else if (valid && u == 0) {
-      a.reward[env] = usum / (float)U;  // mean utility (metrics.py:25-28)
+      a.reward[env] = usum * a.inv_U;  // mean utility (metrics.py:25-28)
     }
     if (a.metrics) {
-      unsigned cm = __ballot_sync(kFull, valid && conn != 0) & segmask;
+      unsigned cm = __ballot_sync(kFull, conn != 0) & segmask;
       float csum = seg_sum_c<U>((float)__popc(conn), u, lane);
       float rsum = seg_sum_c<U>((float)rate, u, lane);
       if (valid && u == 0) {
-        int nc = __popc(cm);
-        reinterpret_cast<float4*>(a.metrics)[env] =
-            make_float4(csum, (float)nc, usum / (float)U, nc ? rsum / (float)nc : 0.0f);
+        float nc = (float)__popc(cm);
+        reinterpret_cast<float4*>(a.metrics)[env] = make_float4(csum, nc, usum * a.inv_U, mean_or_zero(rsum, nc));
       }
     }
     if (valid && a.dbg_snr) {
 #pragma unroll
-      for (int b = 0; b < B; ++b) {
-        const SlotDev& c = slot_of(b);
-        a.dbg_snr[idx * B + b] = (b < nb) ? exp2f(log2_snr_obs(c.k, c.l0, c.l_zero, d2pre[b])) : 0.0f;
-      }
+      for (int b = 0; b < B; ++b)
+        a.dbg_snr[(size_t)idx * B + b] = (b < nb) ? ex2_sfu(log2_snr_obs(C0.k, C0.l0, C0.l_zero, d2pre[b])) : 0.0f;
     }
 
     phase_move();
@@ -252,17 +249,18 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
     if (MA) {
       // statistics change only for envs that ended (connections dropped / fresh episode)
       if (__any_sync(kFull, done)) {
+        if (done && u == 0) {
 #pragma unroll
-        for (int b = 0; b < B; ++b)
-          if (done && u == 0) {
+          for (int b = 0; b < B; ++b) {
             s_bsn[env_in_blk * B + b] = 0;
             s_bsu[env_in_blk * B + b] = -1.0f;
           }
+        }
         __syncwarp();
       }
     }
     if (valid) {
-      float* row = s_obs + ((size_t)env_in_blk * U + u) * F;
+      float* row = s_obs + ((unsigned)env_in_blk * U + u) * F;
       if (done && !fresh) {  // inactive UEs observe zeros
 #pragma unroll
         for (int f = 0; f < F; ++f) row[f] = 0.0f;
@@ -270,20 +268,23 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
         float l[B];
         float lmax = -INFINITY;
         uint32_t elig2 = 0;
+        const float xf = (float)x, yf = (float)y;
 #pragma unroll
         for (int b = 0; b < B; ++b) {
-          const SlotDev& c = slot_of(b);
-          int d2 = d2_to(b);
-          l[b] = log2_snr_obs(c.k, c.l0, c.l_zero, d2);
+          int bx, by;
+          bs_xy_of(b, bx, by);
+          float dx = xf - (float)bx, dy = yf - (float)by;
+          float d2f = fmaf(dx, dx, dy * dy);  // exact: integers below 2^24
+          l[b] = log2_snr_obs_f(C0.k, C0.l0, C0.l_zero, d2f);
           bool live = !PER_ENV || (b < nb);
           if (!live) l[b] = -INFINITY;
           lmax = fmaxf(lmax, l[b]);
-          if (live && d2 <= c.d2max) elig2 |= 1u << b;
+          if (MA && live && d2f <= (float)C0.d2max) elig2 |= 1u << b;
         }
 #pragma unroll
         for (int b = 0; b < B; ++b) {
           row[b] = ((conn >> b) & 1u) ? 1.0f : 0.0f;
-          row[B + b] = exp2f(l[b] - lmax);  // snr / max snr
+          row[B + b] = ex2_sfu(l[b] - lmax);  // snr / max snr
         }
         row[2 * B] = fresh ? -1.0f : util;
         if (MA) {
