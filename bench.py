@@ -150,7 +150,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--preheat-seconds", type=float, default=0.3)
+    ap.add_argument("--preheat-seconds", type=float, default=1.0)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

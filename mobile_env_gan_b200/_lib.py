@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libmbe.so")
+LIB_PATH = os.environ.get("MBE_LIB_PATH") or os.path.join(HERE, "csrc", "libmbe.so")
 
 MBE_ABI_VERSION = 1
 MODE_FORK, MODE_GYM = 0, 1

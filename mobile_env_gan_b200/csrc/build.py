@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libmbe.so")
 SOURCES = ["mbe.cu"]
-DEPS = ["mbe.cu", "mbe_step.cuh", "mbe_device.cuh", os.path.join("..", "..", "include", "mbe.h")]
+DEPS = ["mbe.cu", "mbe_step.cuh", "mbe_step_spec.cuh", "mbe_device.cuh", os.path.join("..", "..", "include", "mbe.h")]
 
 
 def nvcc_path() -> str:
@@ -26,22 +26,22 @@ def is_stale() -> bool:
     return any(os.path.getmtime(os.path.join(HERE, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, out: str = None, defines=()) -> str:
+    if out is None and not force and not is_stale():
         return LIB
     cmd = [
         nvcc_path(), "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
         "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
         "--expt-relaxed-constexpr", "--extended-lambda",
         "-Xptxas", "-v" if verbose else "-O3",
-        "-o", LIB,
-    ] + [os.path.join(HERE, s) for s in SOURCES]
+        "-o", out or LIB,
+    ] + [f"-D{d}" for d in defines] + [os.path.join(HERE, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

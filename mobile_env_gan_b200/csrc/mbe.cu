@@ -1,6 +1,7 @@
 // libmbe.so -- C ABI (include/mbe.h) over the sm_100a kernels in mbe_step.cuh.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -142,6 +143,17 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   a.velocity = cfg->velocity;
   a.velocity_f = (float)cfg->velocity;
   a.tie_eps = (float)(cfg->velocity * 1e-6 + 1e-6);
+  {  // is an axis-aligned step exactly +-velocity in the reference's FP64 chain (movement.py:58-59)?
+    volatile double v = cfg->velocity;
+    int ok = 1;
+    const int dmax = (int)std::max(cfg->width, cfg->height) + 1;
+    for (int d = 1; d <= dmax && ok; ++d) {
+      volatile double prod = v * (double)d;
+      volatile double q = prod / (double)d;
+      if (q != v) ok = 0;
+    }
+    a.axis_exact = ok;
+  }
   a.move_d2max = cfg->move_d2max;
   a.util_c = (float)(cfg->util_w1 * std::log(2.0) / std::log(cfg->util_w3));
   a.util_w2 = (float)cfg->util_w2;
@@ -162,14 +174,16 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     d.stride = h.d2max + 1;
     d.lutn = nullptr;
     if (h.d2max >= 0) {
-      // lutn[(n-1)*stride + d2] = round(rate_lut[d2] / n, 2) in FP64 (schedules.py:20-22, base.py:435)
+      // device table: [0] = 0.0, then rows n = 1..U of round(rate_lut[d2] / n, 2) in FP64
+      // (schedules.py:20-22, base.py:435); kernels index it as lutn[n*stride + d2]
       const int rows = a.U;
-      std::vector<double> tab((size_t)rows * d.stride);
+      std::vector<double> tab((size_t)rows * d.stride + 1);
+      tab[0] = 0.0;
       for (int n = 1; n <= rows; ++n)
         for (int i = 0; i < d.stride; ++i) {
           volatile double share = h.rate_lut[i] / (double)n;
           volatile double scaled = share * 100.0;
-          tab[(size_t)(n - 1) * d.stride + i] = std::nearbyint(scaled) / 100.0;
+          tab[1 + (size_t)(n - 1) * d.stride + i] = std::nearbyint(scaled) / 100.0;
         }
       double* p = nullptr;
       size_t bytes = tab.size() * sizeof(double);
@@ -180,7 +194,7 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
         return fail("mbe_create: rate table upload failed: %s", cudaGetErrorString(e));
       }
       env->luts.push_back(p);
-      d.lutn = p;
+      d.lutn = p + 1 - d.stride;  // biased: row n starts at lutn + n*stride, lutn[stride-1] == 0.0
     }
   }
   if (cfg->bs_class) {
@@ -206,8 +220,7 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     sl.stride = d.stride;
     sl.k = d.k_hi;
     sl.l0 = d.l0_hi;
-    sl.l_zero = d.l_zero;
-    sl.pad = 0.0f;
+    sl.xf = sl.yf = 0.0f;
     sl.lutn = d.lutn;
   }
   // the specialised kernels assume one BS class and squared distances exact in FP32
@@ -294,6 +307,8 @@ int mbe_bind(mbe_env* env, const mbe_buffers* b) {
     for (int i = 0; i < a.B; ++i) {
       a.slot[i].x = xy[2 * i];
       a.slot[i].y = xy[2 * i + 1];
+      a.slot[i].xf = (float)xy[2 * i];
+      a.slot[i].yf = (float)xy[2 * i + 1];
     }
   }
   env->bound = true;
@@ -309,7 +324,8 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
   a.reset_mask = mask;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool gym = env->cfg.mode == MBE_MODE_GYM, ma = env->cfg.handler == MBE_HANDLER_MA;
-  if (env->spec && op == mbe::OP_STEP && phases == MBE_PHASE_ALL)
+  // debug SNR output and waypoint injection only exist in the generic kernel
+  if (env->spec && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr && !a.inj_wp)
     env->spec<<<env->grid, mbe::kThreads, env->spec_smem, st>>>(a);
   else if (!gym)
     mbe::step_kernel<0, 0><<<env->grid, mbe::kThreads, env->smem, st>>>(a);

@@ -6,7 +6,10 @@
 
 namespace mbe {
 
-constexpr int kWarpsPerBlock = 8;
+#ifndef MBE_WARPS_PER_BLOCK
+#define MBE_WARPS_PER_BLOCK 4
+#endif
+constexpr int kWarpsPerBlock = MBE_WARPS_PER_BLOCK;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxSlots = 32;
@@ -22,8 +25,10 @@ struct ClassDev {
   int d2max;           // connectable iff d2 <= d2max
   int stride;          // d2max + 1
   int pad;
-  // lutn[(n-1)*stride + d2] = round(rate_lut[d2] / n, 2): Channel.datarate (channels.py:78-83)
-  // split over n UEs (schedules.py:20-22) and rounded like base.py:435, all in FP64
+  // lutn[n*stride + d2] = round(rate_lut[d2] / n, 2) for n >= 1: Channel.datarate
+  // (channels.py:78-83) split over n UEs (schedules.py:20-22) and rounded like base.py:435, all
+  // in FP64.  Row n = 0 does not exist: the pointer is biased so that lutn[stride - 1] is a
+  // 0.0 entry placed just before row 1 (an unconnected link adds exactly nothing).
   const double* lutn;
 };
 
@@ -31,7 +36,7 @@ struct ClassDev {
 // operand once the specialised kernels unroll their loops over b.
 struct SlotDev {
   int x, y, d2max, stride;
-  float k, l0, l_zero, pad;
+  float k, l0, xf, yf;  // xf, yf: the same coordinates as floats (exact)
   const double* lutn;
 };
 
@@ -47,6 +52,7 @@ struct StepArgs {
   unsigned seed_lo, seed_hi;
   double width, height, velocity;
   float velocity_f, tie_eps;  // FP32 fast path of the movement and its fallback band
+  int axis_exact;             // (velocity*d)/|d| == +-velocity in FP64 for every |d| on the map
   int move_d2max;
   // utility: u = clip(util_c * log2(w2 + r), lo, hi); scaled = (u - lo) * util_scale - 1
   float util_c, util_w2, util_lo, util_hi, util_scale;
@@ -158,7 +164,14 @@ __device__ __forceinline__ bool move_ue(const StepArgs& a, int& x, int& y, int w
   float rx = rintf(tx), ry = rintf(ty);
   float worst = fmaxf(fabsf(tx - rx), fabsf(ty - ry));  // distance to the nearest integer, <= 0.5
   if (worst > 0.5f - a.tie_eps) {
-    move_slow(a, x, y, dx, dy, d2);
+    if (a.axis_exact && (dx == 0 || dy == 0)) {
+      // axis-aligned (frequent: integer snapping lines UEs up with their waypoint): the FP64
+      // step is exactly +-velocity (host-verified), so only the final rint needs FP64
+      if (dx != 0) x = (int)rint((double)x + (dx > 0 ? a.velocity : -a.velocity));
+      if (dy != 0) y = (int)rint((double)y + (dy > 0 ? a.velocity : -a.velocity));
+    } else {
+      move_slow(a, x, y, dx, dy, d2);
+    }
   } else {
     x += (int)rx;
     y += (int)ry;
@@ -174,14 +187,13 @@ __device__ __forceinline__ float log2_snr(const ClassDev& c, int d2) {
   return fmaf(-c.k_lo, lg, l) + c.l0_lo;
 }
 
-// single-float form used for the observation ratios snr/max snr (error < 2e-6 relative)
-__device__ __forceinline__ float log2_snr_obs(float k, float l0, float l_zero, int d2) {
-  return d2 ? fmaf(-k, lg2_sfu((float)d2), l0) : l_zero;
+// single-float form used for the observation ratios snr/max snr (error < 2e-6 relative).
+// d2f is the squared distance in FP32 (exact below 2^24); d = 0 is the reference's EPSILON
+// (channels.py:8): log10(0 + 1e-16) <=> d2 = 1e-32.
+__device__ __forceinline__ float log2_snr_obs_f(float k, float l0, float d2f) {
+  return fmaf(-k, lg2_sfu(fmaxf(d2f, 1e-32f)), l0);
 }
-// same with the squared distance already in FP32 (exact for d2 < 2^24)
-__device__ __forceinline__ float log2_snr_obs_f(float k, float l0, float l_zero, float d2f) {
-  return (d2f > 0.0f) ? fmaf(-k, lg2_sfu(d2f), l0) : l_zero;
-}
+__device__ __forceinline__ float log2_snr_obs(float k, float l0, int d2) { return log2_snr_obs_f(k, l0, (float)d2); }
 
 // BoundedLogUtility.calculateUtility + scaleUtility (utilities.py:44-55); SFU lg2
 // (absolute error 2^-22 near 1, relative 2^-22 elsewhere).
@@ -213,6 +225,17 @@ __device__ __forceinline__ float seg_sum_c(float v, int u, int lane) {
     if (u + off < U) v += o;
   }
   return __shfl_sync(kFull, v, lane - u);
+}
+
+// Same tree without the final broadcast: only the env's first lane (u == 0) holds the sum.
+template <int U>
+__device__ __forceinline__ float seg_sum_head(float v, int u) {
+#pragma unroll
+  for (int off = 1; off < U; off <<= 1) {
+    float o = __shfl_down_sync(kFull, v, off);
+    if (u + off < U) v += o;
+  }
+  return v;
 }
 
 // (Re)initialise one env: MComCore.reset + MComCustom.reset (base.py:172-209, custom.py:40-62).

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     if (valid && best >= 0) {
       int n = __popc(peers);
       const ClassDev& c = a.cls[s.cls[best]];
-      rate = c.lutn[(size_t)(n - 1) * c.stride + bestd2];  // schedules.py:20-22, base.py:435
+      rate = c.lutn[(size_t)n * c.stride + bestd2];  // schedules.py:20-22, base.py:435
     }
     util = scaled_utility(a, rate);
     util_known = true;
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
       if (bit) {  // allocateDataRate2User (base.py:421-435), bs-major accumulation (413-418)
         int n = __popc(m);
         const ClassDev& c = a.cls[s.cls[b]];
-        rate += c.lutn[(size_t)(n - 1) * c.stride + d2_to(b)];
+        rate += c.lutn[(size_t)n * c.stride + d2_to(b)];
       }
     }
     util = scaled_utility(a, rate);
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     for (int b = 0; b < nb; ++b) {
       const ClassDev& c = a.cls[s.cls[b]];
       int d2 = d2_to(b);
-      float l = log2_snr_obs(c.k_hi, c.l0_hi, c.l_zero, d2);
+      float l = log2_snr_obs(c.k_hi, c.l0_hi, d2);
       row[B + b] = l;
       lmax = fmaxf(lmax, l);
       if (d2 <= c.d2max) elig |= 1u << b;

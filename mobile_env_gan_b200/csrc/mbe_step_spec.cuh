@@ -5,9 +5,16 @@
 // (mbe_step.cuh), which remains the path for reset / observe / split phases and for shapes
 // without an instantiation.  Only the whole fused step (OP_STEP, all phases) runs here.
 // Preconditions checked by the dispatcher (mbe.cu): one BS class, width^2+height^2 < 2^24
-// (squared distances are exact in FP32).
+// (squared distances are exact in FP32), no debug SNR output and no waypoint injection bound.
 #pragma once
 #include "mbe_device.cuh"
+
+// Resident CTAs per SM the register allocation is held to: the small shapes run at full
+// occupancy (16 x 128 threads, 32 registers), measured best on B200 (profiles/README.md);
+// the wide shapes keep 64 registers for their per-BS arrays.
+#ifndef MBE_SPEC_MIN_BLOCKS
+#define MBE_SPEC_MIN_BLOCKS(B) ((B) <= 4 ? 16 : 8)
+#endif
 
 namespace mbe {
 
@@ -23,7 +30,7 @@ __host__ __device__ constexpr size_t spec_smem_bytes(bool gym) {
 }
 
 template <int MODE, int HANDLER, int U, int B, bool PER_ENV>
-__global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kThreads, MBE_SPEC_MIN_BLOCKS(B)) step_spec_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool GYM = (MODE == 1);
   constexpr bool MA = (HANDLER == 1);
@@ -105,20 +112,8 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
   };
 
   auto phase_move = [&]() {
-    if (wx < 0) {  // no waypoint: draw one (movement.py:44-47)
-      if (a.inj_wp) {
-        if (valid) {
-          int k = a.wp_cnt[idx];
-          unpack_xy(a.inj_wp[(size_t)idx * a.inj_k + min(k, a.inj_k - 1)], wx, wy);
-          a.wp_cnt[idx] = k + 1;
-        } else {
-          wx = wy = 0;
-        }
-      } else {
-        philox_point(a, gid, (unsigned)u, (unsigned)t_e, P_WAYPOINT, a.reset_rng_episode ? 0u : (unsigned)epi,
-                     wx, wy);
-      }
-    }
+    if (wx < 0)  // no waypoint: draw one (movement.py:44-47)
+      philox_point(a, gid, (unsigned)u, (unsigned)t_e, P_WAYPOINT, a.reset_rng_episode ? 0u : (unsigned)epi, wx, wy);
     if (move_ue(a, x, y, wx, wy)) wx = wy = -1;
   };
 
@@ -148,7 +143,7 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
     const bool has = valid && best >= 0;
     unsigned peers = __match_any_sync(kFull, has ? (seg * 64 + best) : (0x10000 + lane));
     double rate = 0.0;
-    if (has) rate = C0.lutn[(unsigned)(__popc(peers) - 1) * (unsigned)C0.stride + (unsigned)bestd2];
+    if (has) rate = C0.lutn[(unsigned)__popc(peers) * (unsigned)C0.stride + (unsigned)bestd2];
     util = scaled_utility(a, rate);
     if (valid) {
       a.assoc[idx] = best;
@@ -157,17 +152,12 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
     }
     if (a.metrics) {
       unsigned cm = __ballot_sync(kFull, has) & segmask;
-      float usum = seg_sum_c<U>(valid ? util : 0.0f, u, lane);
-      float rsum = seg_sum_c<U>((float)rate, u, lane);
+      float usum = seg_sum_head<U>(valid ? util : 0.0f, u);
+      float rsum = seg_sum_head<U>((float)rate, u);
       if (valid && u == 0) {
         float nc = (float)__popc(cm);
         reinterpret_cast<float4*>(a.metrics)[env] = make_float4(nc, nc, usum * a.inv_U, mean_or_zero(rsum, nc));
       }
-    }
-    if (valid && a.dbg_snr) {
-#pragma unroll
-      for (int b = 0; b < B; ++b)
-        a.dbg_snr[(size_t)idx * B + b] = (b < nb) ? ex2_sfu(log2_snr_obs(C0.k, C0.l0, C0.l_zero, d2_to(b))) : 0.0f;
     }
     phase_clock();
   } else {
@@ -186,16 +176,26 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
       uint32_t bit = 1u << (act - 1);
       conn = (conn & bit) ? (conn & ~bit) : (conn | (elig & bit));
     }
+    // |connections(b)| for every BS of the env, then allocateDataRate2User (base.py:421-435):
+    // the link's share comes from the pre-rounded table, bs-major accumulation (413-418); an
+    // unconnected slot reads the table's 0.0 entry, so the loads need no predication
+    int cnt[B];
+    int csum_i = 0;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      cnt[b] = __popc(__ballot_sync(kFull, (conn >> b) & 1u) & segmask);
+      csum_i += cnt[b];
+    }
+    const double* lut = C0.lutn;
+    const unsigned stride = (unsigned)C0.stride;
     double rate = 0.0;
 #pragma unroll
     for (int b = 0; b < B; ++b) {
-      bool bit = (conn >> b) & 1u;
-      unsigned m = __ballot_sync(kFull, bit) & segmask;
-      if (bit)  // allocateDataRate2User (base.py:421-435), bs-major accumulation (413-418)
-        rate += C0.lutn[(unsigned)(__popc(m) - 1) * (unsigned)C0.stride + (unsigned)d2pre[b]];
+      unsigned off = (unsigned)cnt[b] * stride + (unsigned)d2pre[b];
+      rate += lut[((conn >> b) & 1u) ? off : stride - 1u];
     }
     util = scaled_utility(a, rate);
-    float usum = seg_sum_c<U>(valid ? util : 0.0f, u, lane);
+    float usum = seg_sum_head<U>(valid ? util : 0.0f, u);
     if (valid) {
       if (a.rate) a.rate[idx] = rate;
       a.utility[idx] = util;
@@ -204,10 +204,9 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
 #pragma unroll
       for (int b = 0; b < B; ++b) {
         bool bit = (conn >> b) & 1u;
-        unsigned m = __ballot_sync(kFull, bit) & segmask;
-        float sum = seg_sum_c<U>(bit ? util : 0.0f, u, lane);
+        float sum = seg_sum_head<U>(bit ? util : 0.0f, u);
         if (valid && u == 0) {
-          int n = __popc(m);
+          int n = cnt[b];
           s_bsn[env_in_blk * B + b] = n;
           s_bsu[env_in_blk * B + b] = n ? sum / (float)n : -1.0f;
         }
@@ -229,17 +228,12 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
     }
     if (a.metrics) {
       unsigned cm = __ballot_sync(kFull, conn != 0) & segmask;
-      float csum = seg_sum_c<U>((float)__popc(conn), u, lane);
-      float rsum = seg_sum_c<U>((float)rate, u, lane);
+      float csum = (float)csum_i;
+      float rsum = seg_sum_head<U>((float)rate, u);
       if (valid && u == 0) {
         float nc = (float)__popc(cm);
         reinterpret_cast<float4*>(a.metrics)[env] = make_float4(csum, nc, usum * a.inv_U, mean_or_zero(rsum, nc));
       }
-    }
-    if (valid && a.dbg_snr) {
-#pragma unroll
-      for (int b = 0; b < B; ++b)
-        a.dbg_snr[(size_t)idx * B + b] = (b < nb) ? ex2_sfu(log2_snr_obs(C0.k, C0.l0, C0.l_zero, d2pre[b])) : 0.0f;
     }
 
     phase_move();
@@ -271,11 +265,19 @@ __global__ void __launch_bounds__(kThreads) step_spec_kernel(const __grid_consta
         const float xf = (float)x, yf = (float)y;
 #pragma unroll
         for (int b = 0; b < B; ++b) {
-          int bx, by;
-          bs_xy_of(b, bx, by);
-          float dx = xf - (float)bx, dy = yf - (float)by;
+          float bxf, byf;
+          if (PER_ENV) {
+            int bx, by;
+            unpack_xy(bs_env[b], bx, by);
+            bxf = (float)bx;
+            byf = (float)by;
+          } else {
+            bxf = a.slot[b].xf;
+            byf = a.slot[b].yf;
+          }
+          float dx = xf - bxf, dy = yf - byf;
           float d2f = fmaf(dx, dx, dy * dy);  // exact: integers below 2^24
-          l[b] = log2_snr_obs_f(C0.k, C0.l0, C0.l_zero, d2f);
+          l[b] = log2_snr_obs_f(C0.k, C0.l0, d2f);
           bool live = !PER_ENV || (b < nb);
           if (!live) l[b] = -INFINITY;
           lmax = fmaxf(lmax, l[b]);
