@@ -287,7 +287,7 @@ def main():
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "kernel": "mbe::step_kernel<1,0>",
+                "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "kernel": f"mbe::step_spec_kernel<gym,{handler},U={U},B={B}>",
                 "bytes_per_env_step": bpe["layout"], "bytes_per_env_step_survey_8d": bpe["survey_8d"],
                 "frac_survey_8d": bpe["survey_8d"] * E / per_launch_s / 1e9 / peak,
             },
