@@ -30,7 +30,7 @@ from .channels import Channel, OkumuraHata
 from .entities import BaseStation, UserEquipment
 from .logging import Monitor
 from .movement import Movement, RandomWaypointMovement
-from .schedules import ResourceFair, Scheduler
+from .schedules import ProportionalFair, ResourceFair, Scheduler
 from .util import deep_dict_merge
 from .utilities import BoundedLogUtility, Utility
 
@@ -58,6 +58,7 @@ class Plan:
     velocity: float
     move_d2max: int
     utility: tuple
+    scheduler: int = 0
     classes: List[dict] = field(default_factory=list)
     bs_class: Optional[np.ndarray] = None
     bs_xy: Optional[np.ndarray] = None  # shared layout [B,2] int16
@@ -127,8 +128,9 @@ class MComCore:
         arrival, channel, scheduler, movement, utility = plugins
         if not isinstance(arrival, NoDeparture):
             raise NotImplementedError(f"arrival {type(arrival).__name__}: only NoDeparture has a CUDA kernel")
-        if not isinstance(scheduler, ResourceFair):
-            raise NotImplementedError(f"scheduler {type(scheduler).__name__}: only ResourceFair has a CUDA kernel")
+        if not isinstance(scheduler, (ResourceFair, ProportionalFair)):
+            raise NotImplementedError(
+                f"scheduler {type(scheduler).__name__}: only ResourceFair / ProportionalFair have CUDA kernels")
         if not isinstance(utility, BoundedLogUtility):
             raise NotImplementedError(f"utility {type(utility).__name__}: only BoundedLogUtility has a CUDA kernel")
         if not isinstance(channel, Channel):
@@ -178,7 +180,7 @@ class MComCore:
             env_offset=int(config.get("env_offset", 0)), seed=int(movement.seed),
             width=width, height=height, velocity=mv["velocity"], move_d2max=mv["move_d2max"],
             utility=(float(utility.lower), float(utility.upper), float(w1), float(w2), float(w3)),
-            classes=classes, bs_class=bs_class, bs_xy=bs_xy,
+            scheduler=int(scheduler.kernel_id), classes=classes, bs_class=bs_class, bs_xy=bs_xy,
         )
 
     @staticmethod
@@ -248,7 +250,7 @@ class MComCore:
         cfg.abi_version = _lib.MBE_ABI_VERSION
         cfg.device = self.device.index
         cfg.num_envs, cfg.num_ues, cfg.num_bs = p.num_envs, p.num_ues, p.num_bs
-        cfg.mode, cfg.handler, cfg.scheduler = p.mode, p.handler, _lib.SCHED_RESOURCE_FAIR
+        cfg.mode, cfg.handler, cfg.scheduler = p.mode, p.handler, p.scheduler
         cfg.bs_layout = p.bs_layout
         cfg.bs_random_min, cfg.bs_random_max = p.bs_random
         cfg.autoreset = int(p.autoreset)
@@ -292,7 +294,8 @@ class MComCore:
         self._terminated = z(E, dt=torch.bool)  # no natural termination, only truncation
         self.metrics = z(E, 4, dt=torch.float32)
         gym = p.mode == _lib.MODE_GYM
-        self.conn = z(E, U, dt=torch.int32) if gym else None
+        mw = (B + 31) // 32  # connection bitmask words per UE
+        self.conn = (z(E, U, dt=torch.int32) if mw == 1 else z(E, U, mw, dt=torch.int32)) if gym else None
         self.actions = z(E, U, dt=torch.int32) if gym else None
         self.obs = z(E, U, p.feature_size, dt=torch.float32) if gym else None
         self.reward = (z(E, U, dt=torch.float32) if p.handler == _lib.HANDLER_MA else z(E, dt=torch.float32)) if gym else None

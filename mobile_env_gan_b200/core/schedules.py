@@ -27,6 +27,19 @@ class ResourceFair(Scheduler):
         return [r / n for r in rates]
 
 
+class ProportionalFair(Scheduler):
+    """Not in the fork (its schedules.py has ResourceFair and a broken RateFair only); this build's
+    definition: a UE receives the fraction r_u / sum(r) of its BS, i.e. ``r_u * r_u / total``, with
+    ``total`` accumulated in 2^-20 fixed point so that it does not depend on the summation order
+    (see oracle/mbe_oracle.py:pf_total).  Parity unpinned."""
+
+    kernel_id = 1
+
+    def share(self, bs, rates):
+        total = float(sum(int(round(float(r) * 2.0**20)) for r in rates)) * 2.0**-20
+        return [r * r / total for r in rates]
+
+
 class RateFair(Scheduler):
     """Listed for completeness: the reference's RateFair.share returns a scalar
     (schedules.py:26-29) and cannot be used by allocateDataRate2User (base.py:435)."""

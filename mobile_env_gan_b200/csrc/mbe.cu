@@ -13,6 +13,7 @@
 #include "../../include/mbe.h"
 #include "mbe_step.cuh"
 #include "mbe_step_spec.cuh"
+#include "mbe_step_big.cuh"
 
 namespace {
 
@@ -50,6 +51,7 @@ struct mbe_env {
   void (*spec)(mbe::StepArgs) = nullptr;
   size_t spec_smem = 0;
   int spec_grid = 0;
+  bool big = false;  // block-per-env kernel (wide shapes, ProportionalFair)
 };
 
 namespace {
@@ -92,14 +94,15 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   if (cfg->abi_version != MBE_ABI_VERSION)
     return fail("mbe_create: abi_version %d, library is %d", cfg->abi_version, MBE_ABI_VERSION);
   if (cfg->num_envs <= 0) return fail("mbe_create: num_envs must be > 0");
-  if (cfg->num_ues <= 0 || cfg->num_ues > 32)
-    return fail("mbe_create: num_ues=%d not supported by the warp-segment kernel (1..32)", cfg->num_ues);
-  if (cfg->num_bs <= 0 || cfg->num_bs > 32)
-    return fail("mbe_create: num_bs=%d not supported by the warp-segment kernel (1..32)", cfg->num_bs);
+  if (cfg->num_ues <= 0 || cfg->num_ues > mbe::kBigMaxI * mbe::kBigThreads)
+    return fail("mbe_create: num_ues=%d out of range (1..%d)", cfg->num_ues, mbe::kBigMaxI * mbe::kBigThreads);
+  if (cfg->num_bs <= 0 || cfg->num_bs > mbe::kBigMaxB)
+    return fail("mbe_create: num_bs=%d out of range (1..%d)", cfg->num_bs, mbe::kBigMaxB);
   if (cfg->mode != MBE_MODE_FORK && cfg->mode != MBE_MODE_GYM) return fail("mbe_create: bad mode %d", cfg->mode);
   if (cfg->handler != MBE_HANDLER_CENTRAL && cfg->handler != MBE_HANDLER_MA)
     return fail("mbe_create: bad handler %d", cfg->handler);
-  if (cfg->scheduler != MBE_SCHED_RESOURCE_FAIR) return fail("mbe_create: scheduler %d not available", cfg->scheduler);
+  if (cfg->scheduler != MBE_SCHED_RESOURCE_FAIR && cfg->scheduler != MBE_SCHED_PROPORTIONAL_FAIR)
+    return fail("mbe_create: scheduler %d not available", cfg->scheduler);
   if (cfg->num_classes < 1 || cfg->num_classes > MBE_MAX_CLASSES)
     return fail("mbe_create: num_classes=%d out of range", cfg->num_classes);
   if (!(cfg->width > 0 && cfg->width <= 32767 && cfg->height > 0 && cfg->height <= 32767))
@@ -126,8 +129,10 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   a.U = cfg->num_ues;
   a.B = cfg->num_bs;
   const bool gym = cfg->mode == MBE_MODE_GYM, ma = cfg->handler == MBE_HANDLER_MA;
+  env->big = a.U > 32 || a.B > 32 || cfg->scheduler == MBE_SCHED_PROPORTIONAL_FAIR;
+  a.scheduler = cfg->scheduler;
   a.F = gym ? (ma ? 4 * a.B + 1 : 2 * a.B + 1) : 0;
-  a.epw = 32 / a.U;
+  a.epw = env->big ? 1 : 32 / a.U;
   a.epb = a.epw * mbe::kWarpsPerBlock;
   a.env_offset = (unsigned)cfg->env_offset;
   a.ep_time = cfg->ep_time;
@@ -173,7 +178,20 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     d.d2max = h.d2max;
     d.stride = h.d2max + 1;
     d.lutn = nullptr;
-    if (h.d2max >= 0) {
+    d.lut0 = nullptr;
+    if (h.d2max >= 0) {  // the raw table, for the block-per-env kernel
+      double* p0 = nullptr;
+      size_t bytes0 = (size_t)d.stride * sizeof(double);
+      cudaError_t e0 = cudaMalloc(&p0, bytes0);
+      if (e0 == cudaSuccess) e0 = cudaMemcpy(p0, h.rate_lut, bytes0, cudaMemcpyHostToDevice);
+      if (e0 != cudaSuccess) {
+        mbe_destroy(env);
+        return fail("mbe_create: rate_lut upload failed: %s", cudaGetErrorString(e0));
+      }
+      env->luts.push_back(p0);
+      d.lut0 = p0;
+    }
+    if (h.d2max >= 0 && !env->big) {
       // device table: [0] = 0.0, then rows n = 1..U of round(rate_lut[d2] / n, 2) in FP64
       // (schedules.py:20-22, base.py:435); kernels index it as lutn[n*stride + d2]
       const int rows = a.U;
@@ -236,8 +254,9 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
         break;
       }
   }
-  env->smem = mbe::smem_bytes(gym, ma, a.epb, a.U, a.B, a.F, a.bs_per_env);
-  env->grid = (a.E + a.epb - 1) / a.epb;
+  env->smem = env->big ? 0 : mbe::smem_bytes(gym, ma, a.epb, a.U, a.B, a.F, a.bs_per_env);
+  env->grid = env->big ? a.E : (a.E + a.epb - 1) / a.epb;
+  if (env->big) env->spec = nullptr;
   if (env->smem > 200 * 1024) {
     mbe_destroy(env);
     return fail("mbe_create: needs %zu bytes of shared memory per block", env->smem);
@@ -302,9 +321,9 @@ int mbe_bind(mbe_env* env, const mbe_buffers* b) {
   if (!a.bs_per_env) {
     // a shared layout is constant for the life of the binding: fold the coordinates into the
     // kernel parameters (constant bank) for the specialised kernels
-    int16_t xy[2 * mbe::kMaxSlots];
+    int16_t xy[2 * mbe::kBigMaxB];
     MBE_CUDA(cudaMemcpy(xy, b->bs_xy, sizeof(int16_t) * 2 * a.B, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < a.B; ++i) {
+    for (int i = 0; i < a.B && i < mbe::kMaxSlots; ++i) {
       a.slot[i].x = xy[2 * i];
       a.slot[i].y = xy[2 * i + 1];
       a.slot[i].xf = (float)xy[2 * i];
@@ -324,6 +343,20 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
   a.reset_mask = mask;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool gym = env->cfg.mode == MBE_MODE_GYM, ma = env->cfg.handler == MBE_HANDLER_MA;
+  if (env->big) {
+    if (op == mbe::OP_OBSERVE || (op == mbe::OP_STEP && phases != MBE_PHASE_ALL))
+      return fail("split phases / observe are not available on the block-per-env kernel (wide shapes)");
+    if (a.dbg_snr || a.inj_wp) return fail("debug SNR / waypoint injection are not available for wide shapes");
+    if (!gym)
+      mbe::step_big_kernel<0, 0><<<env->grid, mbe::kBigThreads, 0, st>>>(a);
+    else if (!ma)
+      mbe::step_big_kernel<1, 0><<<env->grid, mbe::kBigThreads, 0, st>>>(a);
+    else
+      mbe::step_big_kernel<1, 1><<<env->grid, mbe::kBigThreads, 0, st>>>(a);
+    MBE_CUDA(cudaGetLastError());
+    env->launches += 1;
+    return 0;
+  }
   // debug SNR output and waypoint injection only exist in the generic kernel
   if (env->spec && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr && !a.inj_wp)
     env->spec<<<env->grid, mbe::kThreads, env->spec_smem, st>>>(a);
@@ -358,6 +391,7 @@ int mbe_channel(mbe_env* env, float* out_snr, uint32_t* out_elig, void* stream) 
   if (!env) return fail("null handle");
   if (!env->bound) return fail("mbe_bind has not been called");
   const mbe::StepArgs& a = env->args;
+  if (out_elig && a.B > 32) return fail("mbe_channel: the connectable bitmask output needs num_bs <= 32");
   const size_t total = (size_t)a.E * a.U;
   const int grid = (int)((total + mbe::kThreads - 1) / mbe::kThreads);
   const size_t smem = 4 * (size_t)(a.bs_per_env ? (mbe::kThreads / a.U + 2) * a.B : a.B) + a.B + 16;

@@ -30,6 +30,7 @@ struct ClassDev {
   // in FP64.  Row n = 0 does not exist: the pointer is biased so that lutn[stride - 1] is a
   // 0.0 entry placed just before row 1 (an unconnected link adds exactly nothing).
   const double* lutn;
+  const double* lut0;  // rate_lut[d2] itself (un-split, un-rounded) for the block-per-env kernel
 };
 
 // One BS slot of a shared layout with its class folded in: every field becomes a constant-bank
@@ -58,6 +59,7 @@ struct StepArgs {
   float util_c, util_w2, util_lo, util_hi, util_scale;
   float inv_U;  // 1/U for the per-env means
   int n_classes;
+  int scheduler;  // 0 ResourceFair, 1 ProportionalFair (block-per-env kernel only)
   ClassDev cls[8];
   SlotDev slot[kMaxSlots];
   const uint8_t* bs_class;  // device [B] or nullptr

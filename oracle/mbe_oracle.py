@@ -57,6 +57,7 @@ class Params:
     util_lower: float = -20.0
     util_upper: float = 20.0
     util_coeffs: Sequence[float] = (10.0, 0.0, 10.0)
+    scheduler: str = "resource_fair"  # or "proportional_fair" (not in the fork; spec below)
 
 
 # --------------------------------------------------------------------------------------
@@ -95,6 +96,19 @@ def utility_of(p: Params, rate: float) -> float:
 def scale_utility(p: Params, u: float) -> float:
     """BoundedLogUtility.scaleUtility, reference core/utilities.py:54-55."""
     return 2 * (u - p.util_lower) / (p.util_upper - p.util_lower) - 1
+
+
+PF_SCALE = 2.0**20
+
+
+def pf_total(rates) -> float:
+    """ProportionalFair denominator.  The fork has no ProportionalFair (core/schedules.py holds
+    ResourceFair and a broken RateFair only), so this is the build's specification (parity
+    unpinned): every UE of a BS gets the fraction r_u / sum(r) of the BS's resources, i.e.
+    ``share_u = r_u * r_u / total``.  To make ``total`` independent of the summation order (the
+    reference iterates a Python set) it is accumulated in 2^-20 fixed point:
+    ``total = float(sum(int(rint(r * 2^20)))) * 2^-20``."""
+    return float(sum(int(np.rint(np.float64(r) * PF_SCALE)) for r in rates)) * (1.0 / PF_SCALE)
 
 
 def int_point_dist(ax, ay, bx, by) -> float:
@@ -212,7 +226,11 @@ class ScalarEnv:
         for b, ues in enumerate(bs_conns):
             snrs = [self.snr(b, u) for u in ues]
             max_alloc = [datarate_of(self.p, s) for s in snrs]
-            rates = [r / len(max_alloc) for r in max_alloc]  # ResourceFair, schedules.py:20-22
+            if self.p.scheduler == "proportional_fair":
+                tot = pf_total(max_alloc)
+                rates = [np.float64(r) * np.float64(r) / tot for r in max_alloc]
+            else:
+                rates = [r / len(max_alloc) for r in max_alloc]  # ResourceFair, schedules.py:20-22
             for u, r in zip(ues, rates):
                 pair[(b, u)] = round(np.float64(r), 2)  # np.float64.__round__
         total = {}
@@ -401,8 +419,14 @@ def batch_allocate(p: Params, snr, conn):
     n = conn.sum(axis=1, keepdims=True)  # [E,1,B]
     with np.errstate(over="ignore"):
         raw = np.where(snr > p.snr_tr, p.bw * np.log2(1 + snr), 0.0)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        share = np.where(conn, raw / n, 0.0)
+    if p.scheduler == "proportional_fair":
+        fixed = np.where(conn, np.rint(raw * PF_SCALE), 0.0).astype(np.int64)
+        tot = fixed.sum(axis=1, keepdims=True).astype(np.float64) * (1.0 / PF_SCALE)  # [E,1,B]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            share = np.where(conn, raw * raw / tot, 0.0)
+    else:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            share = np.where(conn, raw / n, 0.0)
     pair = np.round(share, 2)
     total = np.zeros(pair.shape[:2])
     for b in range(pair.shape[2]):  # bs-major accumulation order

@@ -15,6 +15,7 @@ def params_from_env(env) -> orc.Params:
         velocity=cfg["ue"]["velocity"], snr_tr=cfg["ue"]["snr_tr"], noise=cfg["ue"]["noise"],
         ue_height=cfg["ue"]["height"], util_lower=cfg["utility_params"]["lower"],
         util_upper=cfg["utility_params"]["upper"], util_coeffs=tuple(cfg["utility_params"]["coeffs"]),
+        scheduler="proportional_fair" if p.scheduler == 1 else "resource_fair",
     )
 
 
@@ -126,6 +127,15 @@ class Mirror:
         out["pos_after"] = self.pos.copy()
         out["conn_after"] = self.conn.copy()
         return out
+
+
+def conn_bool_from_words(words, B):
+    """GPU connection words (int32 [E,U] or [E,U,MW]) -> bool [E,U,B]."""
+    w = np.asarray(words).astype(np.int64) & 0xFFFFFFFF
+    if w.ndim == 2:
+        w = w[:, :, None]
+    b = np.arange(B)
+    return ((w[:, :, b // 32] >> (b % 32)[None, None, :]) & 1).astype(bool)
 
 
 def conn_bits(conn_bool):

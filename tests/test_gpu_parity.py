@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from conftest import golden_names, golden_waypoints, load_golden
-from mirror import Mirror, conn_bits
+from mirror import Mirror, conn_bits, conn_bool_from_words
 
 pytestmark = pytest.mark.gpu
 
@@ -335,12 +335,91 @@ def test_step_host_roundtrip():
     assert torch.equal(obs_h, obs.cpu()) and torch.equal(rew_h, rew.cpu()) and torch.equal(done_h.bool(), trunc.cpu())
 
 
+# ------------------------------------------------- wide shapes / ProportionalFair (block-per-env)
+WIDE = {
+    # name: (B, U, map, scheduler)
+    "wide_rf": (40, 70, 200, "rf"),
+    "wide_pf": (40, 70, 200, "pf"),
+    "medium_pf": (4, 15, 200, "pf"),
+    "synthetic": (64, 512, 800, "pf"),  # BASELINE.json configs[4]
+    "many_ue": (8, 1024, 300, "rf"),
+}
+
+
+def wide_env(name, mode, handler, E, autoreset, extra=None):
+    from mobile_env_gan_b200.core.schedules import ProportionalFair, ResourceFair
+
+    B, U, size, sched = WIDE[name]
+    rng = np.random.default_rng(B * 1000 + U)
+    bs = rng.integers(0, size, size=(B, 2)).tolist()
+    cfg = {"num_envs": E, "mode": mode, "handler": handler, "autoreset": autoreset, "width": size, "height": size,
+           "movement_params": {"width": size, "height": size, "reset_rng_episode": False},
+           "EP_MAX_TIME": 7, "arrival_params": {"ep_time": 7}, "ue": {"velocity": 9},
+           "scheduler": ProportionalFair if sched == "pf" else ResourceFair}
+    cfg.update(extra or {})
+    return make_env(bs, U, cfg), B, U
+
+
+@pytest.mark.parametrize("handler", ["central", "ma"])
+@pytest.mark.parametrize("name", list(WIDE))
+def test_wide_gym_matches_oracle(name, handler):
+    E = 24 if name in ("synthetic", "many_ue") else 96
+    env, B, U = wide_env(name, "gym", handler, E, autoreset=True)
+    mir = Mirror(env)
+    obs, _ = env.reset()
+    close(obs.cpu().numpy().reshape(E, U, -1), mir.reset(), "reset obs")
+    rng = np.random.default_rng(17)
+    for k in range(16):
+        acts = rng.integers(0, B + 1, size=(E, U)).astype(np.int32)
+        obs, rew, _, trunc, _ = env.step(torch.from_numpy(acts).to(env.device))
+        out = mir.step_gym(acts)
+        assert np.array_equal(conn_bool_from_words(env.conn.cpu().numpy(), B), out["conn_after"]), k
+        assert np.array_equal(env.pos.cpu().numpy(), out["pos_after"]), k
+        assert np.array_equal(trunc.cpu().numpy(), out["done"]), k
+        assert np.array_equal(env.rate.cpu().numpy(), out["rate"]), k  # FP64, bit-exact (RF and PF)
+        close(env.utility_scaled.cpu(), out["utility"], f"utility {k}")
+        close(rew.cpu(), out["reward"], f"reward {k}")
+        close(obs.cpu().numpy().reshape(E, U, -1), out["obs"], f"obs {k}")
+        m = env.metrics.cpu().numpy()
+        assert np.array_equal(m[:, 0], out["n_connections"]) and np.array_equal(m[:, 1], out["n_connected"])
+        close(m[:, 2], out["mean_utility"])
+        close(m[:, 3], out["mean_datarate"])
+
+
+@pytest.mark.parametrize("name", ["wide_rf", "wide_pf", "many_ue"])
+def test_wide_fork_matches_oracle(name):
+    E = 40
+    env, B, U = wide_env(name, "fork", "central", E, autoreset=False)
+    mir = Mirror(env)
+    env.reset(), mir.reset()
+    for k in range(7):
+        env.step(0, k)
+        out = mir.step_fork()
+        assert np.array_equal(env.assoc.cpu().numpy(), out["assoc"]), k
+        assert np.array_equal(env.rate.cpu().numpy(), out["rate"]), k
+        assert np.array_equal(env.pos.cpu().numpy(), out["pos_after"]), k
+        assert np.array_equal(env.done.cpu().numpy().astype(bool), out["done"]), k
+        close(env.utility_scaled.cpu(), out["utility"], f"utility {k}")
+        m = env.metrics.cpu().numpy()
+        assert np.array_equal(m[:, 1], out["n_connected"])
+        close(m[:, 3], out["mean_datarate"])
+
+
+def test_wide_connection_mask_has_two_words():
+    env, B, U = wide_env("wide_rf", "gym", "central", 8, autoreset=False)
+    assert env.plan.num_ues == 70 and env.conn.dim() == 3 and env.conn.shape[2] == 2
+
+
 def test_errors_are_loud():
     MComCore, BaseStation, UserEquipment = _mods()
     from mobile_env_gan_b200._lib import MbeError
 
     with pytest.raises(MbeError):
-        make_env(SCENARIOS["small"][0], 40, {"num_envs": 4})  # U > 32 has no kernel yet
+        make_env(SCENARIOS["small"][0], 2000, {"num_envs": 4})  # U > 1024 has no kernel
+    wide, _, _ = wide_env("wide_rf", "gym", "central", 4, autoreset=False)
+    wide.reset()
+    with pytest.raises(MbeError):
+        wide.stage(1)  # split phases only exist on the warp-segment kernels
     env = make_env(SCENARIOS["small"][0], 5, {"num_envs": 4})
     with pytest.raises(RuntimeError):
         env.step(0, 0)  # reset() first

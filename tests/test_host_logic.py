@@ -134,7 +134,7 @@ def test_library_rejects_bad_configs_without_a_gpu():
     assert lib.mbe_create(ctypes.byref(cfg), ctypes.byref(handle)) != 0
     assert b"abi_version" in lib.mbe_last_error()
     cfg.abi_version = _lib.MBE_ABI_VERSION
-    cfg.num_envs, cfg.num_ues, cfg.num_bs = 4, 64, 4
+    cfg.num_envs, cfg.num_ues, cfg.num_bs = 4, 5000, 4
     assert lib.mbe_create(ctypes.byref(cfg), ctypes.byref(handle)) != 0
     assert b"num_ues" in lib.mbe_last_error()
     assert lib.mbe_step(None, None) != 0
