@@ -32,7 +32,7 @@ if ROOT not in sys.path:
 
 METRIC = "env-steps/sec (batched, whole box) for mobile-medium at 1/2/4/8 B200"
 UNIT = "env-steps/s"
-SIZES = {"mobile-small": (3, 5), "mobile-medium": (4, 15), "mobile-large": (13, 30)}
+SIZES = {"mobile-small": (3, 5), "mobile-medium": (4, 15), "mobile-large": (13, 30), "mobile-synthetic": (64, 512)}
 
 
 def bytes_per_env_step(U: int, B: int, handler: str) -> dict:
@@ -287,7 +287,7 @@ def main():
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "kernel": f"mbe::step_spec_kernel<gym,{handler},U={U},B={B}>",
+                "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "kernel": (f"mbe::step_spec_kernel<gym,{handler},U={U},B={B}>" if U <= 32 and B <= 32 else f"mbe::step_big_kernel<gym,{handler}> U={U} B={B}"),
                 "bytes_per_env_step": bpe["layout"], "bytes_per_env_step_survey_8d": bpe["survey_8d"],
                 "frac_survey_8d": bpe["survey_8d"] * E / per_launch_s / 1e9 / peak,
             },

@@ -24,6 +24,7 @@ struct BigSmem {
   int red_i[2][kBigThreads / 32];
   float usum, rsum;
   int csum, ncon;
+  float tile[kBigThreads / 32][32][33];  // per-warp transpose tile of the observation writer
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -342,40 +343,59 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
   }
 
   // ---- POST: observation rows (GYM) ----
+  // A lane owns one UE row of F floats; rows of the warp's 32 UEs are contiguous in HBM.  Features
+  // are produced 32 columns at a time into a padded shared tile and written back transposed, so
+  // every global store instruction covers 128 contiguous bytes of one row.
   if (GYM && touched) {
+    float (*tile)[33] = s.tile[warp];
 #pragma unroll
     for (int i = 0; i < kBigMaxI; ++i) {
-      const int u = tid + i * kBigThreads;
-      if (u >= U) continue;
-      float* row = a.obs + ((size_t)env * U + u) * F;
-      if (done && !fresh) {
-        for (int f = 0; f < F; ++f) row[f] = 0.0f;
-        continue;
-      }
+      const int u0 = warp * 32 + i * kBigThreads;  // first UE of this warp's row group
+      if (u0 >= U) continue;                        // warp-uniform
+      const int u = u0 + lane;
+      const bool live_ue = u < U;
+      const bool zero_row = done && !fresh;
       float lmax = -INFINITY;
-      for (int b = 0; b < nb; ++b) {
-        const ClassDev& c = a.cls[s.cls[b]];
-        lmax = fmaxf(lmax, log2_snr_obs(c.k_hi, c.l0_hi, d2_to(i, b)));
-      }
-      float tot = 0.0f;
-      for (int b = 0; b < B; ++b) {
-        const bool live = b < nb;
-        const ClassDev& c = a.cls[s.cls[b]];
-        const int d2 = live ? d2_to(i, b) : 0;
-        row[b] = has_bit(c0[i], c1[i], b) ? 1.0f : 0.0f;
-        row[B + b] = live ? ex2_sfu(log2_snr_obs(c.k_hi, c.l0_hi, d2) - lmax) : 0.0f;  // snr / max snr
-        if (MA) {
-          const bool ok = live && d2 <= c.d2max;
-          const float n = ok ? (float)s.cnt[b] : 0.0f;
-          row[2 * B + 1 + b] = ok ? s.bsu[b] : -1.0f;
-          row[3 * B + 1 + b] = n;
-          tot += n;
+      if (live_ue && !zero_row)
+        for (int b = 0; b < nb; ++b) {
+          const ClassDev& c = a.cls[s.cls[b]];
+          lmax = fmaxf(lmax, log2_snr_obs(c.k_hi, c.l0_hi, d2_to(i, b)));
         }
-      }
-      row[2 * B] = (fresh || t_e == 0) ? -1.0f : util[i];
-      if (MA) {
-        const float inv = 1.0f / fmaxf(1.0f, tot);
-        for (int b = 0; b < B; ++b) row[3 * B + 1 + b] *= inv;
+      float tot = 0.0f;  // MA: sum of the broadcast connection counts of the connectable BSs
+      if (MA && live_ue && !zero_row)
+        for (int b = 0; b < nb; ++b)
+          if (d2_to(i, b) <= a.cls[s.cls[b]].d2max) tot += (float)s.cnt[b];
+      const float inv_tot = 1.0f / fmaxf(1.0f, tot);
+      float* gbase = a.obs + ((size_t)env * U + u0) * F;
+      for (int f0 = 0; f0 < F; f0 += 32) {
+        for (int j = 0; j < 32; ++j) {
+          const int f = f0 + j;  // warp-uniform feature index
+          float v = 0.0f;
+          if (f < F && live_ue && !zero_row) {
+            if (f < B) {
+              v = has_bit(c0[i], c1[i], f) ? 1.0f : 0.0f;
+            } else if (f < 2 * B) {
+              const int b = f - B;
+              if (b < nb) {
+                const ClassDev& c = a.cls[s.cls[b]];
+                v = ex2_sfu(log2_snr_obs(c.k_hi, c.l0_hi, d2_to(i, b)) - lmax);  // snr / max snr
+              }
+            } else if (f == 2 * B) {
+              v = (fresh || t_e == 0) ? -1.0f : util[i];
+            } else {
+              const int b = (f - 2 * B - 1) % B;
+              const bool ok = (b < nb) && d2_to(i, b) <= a.cls[s.cls[b]].d2max;
+              if (f < 3 * B + 1) v = ok ? s.bsu[b] : -1.0f;
+              else v = ok ? (float)s.cnt[b] * inv_tot : 0.0f;
+            }
+          }
+          tile[lane][j] = v;
+        }
+        __syncwarp();
+        const int f = f0 + lane;
+        for (int r = 0; r < 32; ++r)
+          if (f < F && u0 + r < U) gbase[(size_t)r * F + f] = tile[r][lane];
+        __syncwarp();
       }
     }
   }

@@ -2,7 +2,7 @@
 installed the same ids are also registered there (entry points return the batched env)."""
 from __future__ import annotations
 
-from .scenarios import MComCustom, MComLarge, MComMedium, MComSmall
+from .scenarios import MComCustom, MComLarge, MComMedium, MComSmall, MComSynthetic
 
 _REGISTRY = {}
 
@@ -24,7 +24,8 @@ def make(env_id: str, **kwargs):
     return entry(config=config, **kwargs)
 
 
-for _size, _cls in (("small", MComSmall), ("medium", MComMedium), ("large", MComLarge)):
+for _size, _cls in (("small", MComSmall), ("medium", MComMedium), ("large", MComLarge),
+                    ("synthetic", MComSynthetic)):
     for _h in ("central", "ma"):
         register(f"mobile-{_size}-{_h}-v0", _cls, config={"handler": _h, "mode": "gym"})
 register("mobile-custom-v0", MComCustom)

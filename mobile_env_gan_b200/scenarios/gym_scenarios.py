@@ -42,3 +42,21 @@ class MComMedium(_GymScenario):
 class MComLarge(_GymScenario):
     STATIONS = tuple((20 + 45 * (i % 4) + (22 if (i // 4) % 2 else 0), 25 + 50 * (i // 4)) for i in range(13))
     NUM_UES = 30
+
+
+class MComSynthetic(_GymScenario):
+    """Synthetic scale-up of BASELINE.json configs[4]: 64 BSs x 512 UEs on an 800 x 800 map with the
+    ProportionalFair scheduler; BS coordinates are a fixed pseudo-random integer layout."""
+
+    NUM_UES = 512
+    SIZE = 800
+    STATIONS = tuple(((i * 7919 + 13) % 800, (i * 104729 + 71) % 800) for i in range(64))
+
+    @classmethod
+    def default_config(cls):
+        from ..core.schedules import ProportionalFair
+
+        config = super().default_config()
+        config.update({"width": cls.SIZE, "height": cls.SIZE, "scheduler": ProportionalFair})
+        config["movement_params"].update({"width": cls.SIZE, "height": cls.SIZE})
+        return config
