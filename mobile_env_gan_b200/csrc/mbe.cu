@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -51,6 +52,9 @@ struct mbe_env {
   void (*spec)(mbe::StepArgs) = nullptr;
   size_t spec_smem = 0;
   int spec_grid = 0;
+  void (*pipe)(mbe::StepArgs) = nullptr;
+  size_t pipe_smem = 0;
+  int pipe_grid = 0;
   bool big = false;  // block-per-env kernel (wide shapes, ProportionalFair)
 };
 
@@ -60,12 +64,16 @@ struct SpecEntry {
   int mode, handler, U, B, per_env;
   void (*fn)(mbe::StepArgs);
   size_t smem;
+  void (*pipe_fn)(mbe::StepArgs);  // persistent, TMA-pipelined variant (E % EPB == 0)
+  size_t pipe_smem;
 };
 
 #define MBE_SPEC(MODE, HANDLER, U, B, PE)                                             \
   SpecEntry {                                                                         \
     MODE, HANDLER, U, B, PE, mbe::step_spec_kernel<MODE, HANDLER, U, B, (PE != 0)>,   \
-        mbe::spec_smem_bytes<HANDLER, U, B, (PE != 0)>(MODE == 1)                     \
+        mbe::spec_smem_bytes<HANDLER, U, B, (PE != 0)>(MODE == 1),                    \
+        mbe::step_pipe_kernel<MODE, HANDLER, U, B, (PE != 0)>,                        \
+        mbe::pipe_smem_bytes<HANDLER, U, B, (PE != 0)>(MODE == 1)                     \
   }
 
 // shapes with a compile-time specialisation: the scenario sizes of BASELINE.json (small 3x5,
@@ -251,6 +259,10 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
           sp.per_env == a.bs_per_env) {
         env->spec = sp.fn;
         env->spec_smem = sp.smem;
+        if (a.E % a.epb == 0) {
+          env->pipe = sp.pipe_fn;
+          env->pipe_smem = sp.pipe_smem;
+        }
         break;
       }
   }
@@ -267,6 +279,22 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   if (e == cudaSuccess && env->spec)
     e = cudaFuncSetAttribute((const void*)env->spec, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)env->spec_smem);
+  if (e == cudaSuccess && env->pipe) {
+    // measured slower than the one-chunk-per-CTA kernel on B200 (profiles/README.md): opt-in only
+    const char* v = std::getenv("MBE_PIPE");
+    if (!(v && v[0] == '1')) env->pipe = nullptr;
+  }
+  if (e == cudaSuccess && env->pipe) {
+    e = cudaFuncSetAttribute((const void*)env->pipe, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)env->pipe_smem);
+    int per_sm = 0, sms = 0;
+    if (e == cudaSuccess)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)env->pipe, mbe::kThreads,
+                                                        env->pipe_smem);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    // persistent grid: one full wave of resident CTAs, never more CTAs than chunks
+    env->pipe_grid = std::max(1, std::min(a.E / a.epb, per_sm * sms));
+  }
   if (e != cudaSuccess) {
     mbe_destroy(env);
     return fail("mbe_create: cudaFuncSetAttribute(%zu B smem): %s", env->smem, cudaGetErrorString(e));
@@ -359,7 +387,24 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
   }
   // debug SNR output and waypoint injection only exist in the generic kernel
   if (env->spec && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr && !a.inj_wp)
-    env->spec<<<env->grid, mbe::kThreads, env->spec_smem, st>>>(a);
+  {
+    static const bool pdl = []() {
+      const char* v = std::getenv("MBE_PDL");
+      return !(v && v[0] == '0');
+    }();
+    cudaLaunchConfig_t lc = {};
+    const bool use_pipe = env->pipe != nullptr;
+    lc.gridDim = dim3(use_pipe ? env->pipe_grid : env->grid);
+    lc.blockDim = dim3(mbe::kThreads);
+    lc.dynamicSmemBytes = use_pipe ? env->pipe_smem : env->spec_smem;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = pdl ? 1 : 0;
+    MBE_CUDA(cudaLaunchKernelEx(&lc, use_pipe ? env->pipe : env->spec, a));
+  }
   else if (!gym)
     mbe::step_kernel<0, 0><<<env->grid, mbe::kThreads, env->smem, st>>>(a);
   else if (!ma)

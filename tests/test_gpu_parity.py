@@ -251,6 +251,46 @@ def test_specialised_kernels_equal_generic(scen, mode, handler):
                 assert torch.equal(ta, tb), (name, k)
 
 
+def test_pipelined_variant_matches_default():
+    """MBE_PIPE=1 selects the persistent TMA-pipelined kernels (mbarrier-tracked bulk loads of the
+    next chunk, double-buffered bulk stores).  Kept as a measured design alternative; it must stay
+    bit-identical to the default kernels."""
+    import os
+    import subprocess
+    import sys
+
+    code = """
+import sys, torch, hashlib
+sys.path.insert(0, %r)
+import mobile_env_gan_b200 as mbe
+out = []
+for wid, kw in (("mobile-medium-central-v0", {}), ("mobile-large-ma-v0", {}), ("mobile-custom-v0", {})):
+    env = mbe.make(wid, num_envs=4096, autoreset=True, **kw)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    h = hashlib.sha256()
+    for k in range(45):
+        if env.actions is not None:
+            B = env.plan.num_bs
+            env.step(torch.randint(0, B + 1, env.actions.shape, generator=g, device="cuda", dtype=torch.int32))
+        else:
+            env.step(0, k)
+        for name in ("pos", "wp", "t", "episode", "rate", "utility_scaled", "done", "conn", "assoc", "obs", "reward", "metrics"):
+            t = getattr(env, name)
+            if t is not None:
+                h.update(t.cpu().numpy().tobytes())
+    out.append(h.hexdigest())
+print(" ".join(out))
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, MBE_PIPE=flag)
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        digests.append(res.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1]
+
+
 def test_movement_fast_path_is_exact():
     """The FP32 fast path of the movement falls back to the reference's FP64 chain near rounding
     ties; positions must equal the oracle for awkward velocities (exact .5 ties with v=1.5)."""
