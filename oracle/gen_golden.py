@@ -101,5 +101,53 @@ def main():
         print(name, "steps", steps, "bytes", os.path.getsize(path))
 
 
+def dump_golden(name="kat1", steps=20):
+    """Runs the reference with its JSON/CSV dumps ENABLED (base.py:261,298-404; custom.py:79-85)
+    in a scratch directory and copies the files into tests/golden/dumps/<name>/ -- the byte-level
+    target of mobile_env_gan_b200/export.py."""
+    import shutil
+    import tempfile
+
+    base, entities, custom = rh.import_reference()
+    bs_xy, nue, cfg, _ = CASES[name]
+
+    class DumpingEnv(base.MComCore):
+        def reset(self, *, seed=None):
+            super().reset(seed=seed)
+            users = [ue for ue in self.userDict.values() if ue.startTime <= 0]
+            self.activeUsers = sorted(users, key=lambda ue: ue.ue_id)
+            self.users_dataRateList = {ue.ue_id: [] for ue in self.userDict.values()}
+            self.users_trajectoryList = {ue.ue_id: [] for ue in self.userDict.values()}
+
+    full = DumpingEnv.default_config()
+    from mobile_env.core.util import deep_dict_merge
+
+    full = deep_dict_merge(full, cfg)
+    stations = [entities.BaseStation(i, tuple(xy), **full["bs"]) for i, xy in enumerate(bs_xy)]
+    users = [entities.UserEquipment(i, **full["ue"]) for i in range(nue)]
+    env = DumpingEnv(stations, users, cfg)
+    tmp = tempfile.mkdtemp()
+    run = os.path.join(tmp, "run")
+    os.makedirs(run)
+    cwd = os.getcwd()
+    os.chdir(run)
+    try:
+        env.reset()
+        custom.MComCustom.save_base_station_positions(env, 0)
+        for s in range(steps):
+            env.step(0, s)
+        env.save_epoch_data(0)
+    finally:
+        os.chdir(cwd)
+    dst = os.path.join(OUT, "dumps", name)
+    shutil.rmtree(dst, ignore_errors=True)
+    for sub in ("collectData", "collectData2"):
+        shutil.copytree(os.path.join(tmp, sub), os.path.join(dst, sub))
+    shutil.rmtree(tmp)
+    n = sum(len(f) for _, _, f in os.walk(dst))
+    print("dumps", name, n, "files")
+
+
 if __name__ == "__main__":
     main()
+    dump_golden("kat1")

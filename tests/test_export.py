@@ -1,0 +1,125 @@
+"""Dump formats: mobile_env_gan_b200/export.py against files written by the
+unmodified reference (tests/golden/dumps/kat1, produced by oracle/gen_golden.py:dump_golden with the
+reference's own save_layout_and_data_rates / save_epoch_data / save_base_station_positions)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR, golden_waypoints, load_golden
+from oracle import mbe_oracle as orc
+
+DUMPS = os.path.join(GOLDEN_DIR, "dumps", "kat1")
+
+
+def read(rel):
+    with open(os.path.join(DUMPS, rel)) as f:
+        return f.read()
+
+
+def check_against_reference_files(files):
+    """files: {relative path: text} for epoch/env 0 of the kat1 episode."""
+    n = 0
+    for rel, text in files.items():
+        ref = read(rel)
+        if os.sep + "DataRate" + os.sep + "data_rates_" in rel:
+            # the reference lists the UEs of a BS in Python-set order; compare order-insensitively
+            key = lambda d: (d["bs_id"], d["ue_id"])  # noqa: E731
+            assert sorted(json.loads(text), key=key) == sorted(json.loads(ref), key=key), rel
+            assert text.count("\n") == ref.count("\n")
+        else:
+            assert text == ref, rel
+        n += 1
+    return n
+
+
+def replay_kat1():
+    rec = load_golden("kat1")
+    p = orc.Params(**rec["params"])
+    seq = golden_waypoints(rec)
+    env = orc.ScalarEnv(p, rec["bs_xy"], len(rec["init_pos"]), wp_source=lambda u, k: seq[u][k])
+    env.reset(rec["init_pos"])
+    steps = []
+    for _ in rec["steps"]:
+        out = env.step_fork()
+        steps.append({"pos": out["pos"], "arrived": [w is None for w in env.wp], "assoc": out["assoc"], "rate": out["rate"]})
+    return rec, p, steps
+
+
+def test_formatters_reproduce_reference_dump_files_byte_for_byte():
+    from mobile_env_gan_b200.export import format_epoch_files, format_step_files
+
+    rec, p, steps = replay_kat1()
+    util = (p.util_lower, p.util_upper, tuple(p.util_coeffs))
+    util = (int(util[0]), int(util[1]), tuple(int(c) for c in util[2]))  # reference config holds ints (base.py:136)
+    n = 0
+    for s, st in enumerate(steps):
+        n += check_against_reference_files(format_step_files(0, s, rec["bs_xy"], st["pos"], st["assoc"], st["rate"], util))
+    n += check_against_reference_files(format_epoch_files(
+        0, rec["bs_xy"], [st["pos"] for st in steps], [st["arrived"] for st in steps],
+        [st["assoc"] for st in steps], [st["rate"] for st in steps], util))
+    assert n == 84  # every file the reference wrote for the episode
+
+
+@pytest.mark.gpu
+def test_gpu_writer_reproduces_reference_dump_files(tmp_path):
+    import torch
+
+    from mobile_env_gan_b200.core.base import MComCore
+    from mobile_env_gan_b200.core.entities import BaseStation, UserEquipment
+    from mobile_env_gan_b200.core.util import deep_dict_merge
+    from mobile_env_gan_b200.export import ReferenceDumpWriter
+
+    rec = load_golden("kat1")
+    pr = rec["params"]
+    E, U = 6, len(rec["init_pos"])
+    config = {"num_envs": E, "mode": "fork", "bs": {"tx": pr["tx"]}, "ue": {"velocity": pr["velocity"], "height": pr["ue_height"]}}
+    cfg = deep_dict_merge(MComCore.default_config(), config)
+    stations = [BaseStation(i, tuple(xy), **cfg["bs"]) for i, xy in enumerate(rec["bs_xy"])]
+    users = [UserEquipment(i, **cfg["ue"]) for i in range(U)]
+    env = MComCore(stations, users, config)
+    seq = golden_waypoints(rec)
+    K = max(len(s) for s in seq)
+    wp = np.zeros((E, U, K, 2), dtype=np.int16)
+    for u, s in enumerate(seq):
+        for k, w in enumerate(s):
+            wp[:, u, k] = w
+    env.reset()
+    env.inject_waypoints(wp)
+    env.set_positions(np.broadcast_to(np.array(rec["init_pos"]), (E, U, 2)).copy())
+    writer = ReferenceDumpWriter(env, str(tmp_path), envs=[0, 5])  # env index plays the epoch number
+    writer.begin_episode()
+    for s in range(len(rec["steps"])):
+        env.step(0, s)
+        writer.after_step(s)
+    writer.end_episode()
+    writer.close()
+    files = {}
+    for dirpath, _, names in os.walk(tmp_path):
+        for name in names:
+            full = os.path.join(dirpath, name)
+            files[os.path.relpath(full, tmp_path)] = open(full).read()
+    assert len(files) == 2 * 84
+    import re
+
+    def epoch_of(rel):
+        base = os.path.basename(rel)
+        m = re.search(r"_(\d+)_(\d+)\.json$", base) if rel.startswith("collectData" + os.sep) else None
+        if m:
+            return int(m.group(1))
+        return int(re.search(r"_(\d+)\.(csv|json)$", base).group(1))
+
+    def with_epoch(rel, e):
+        base = os.path.basename(rel)
+        if rel.startswith("collectData" + os.sep):
+            base = re.sub(r"_(\d+)_(\d+)\.json$", lambda m: f"_{e}_{m.group(2)}.json", base)
+        else:
+            base = re.sub(r"_(\d+)\.(csv|json)$", lambda m: f"_{e}.{m.group(2)}", base)
+        return os.path.join(os.path.dirname(rel), base)
+
+    epoch0 = {rel: text for rel, text in files.items() if epoch_of(rel) == 0}
+    assert check_against_reference_files(epoch0) == 84
+    # env 5 ran the same episode: identical contents under its own epoch number
+    for rel, text in epoch0.items():
+        assert files[with_epoch(rel, 5)] == text
