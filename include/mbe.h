@@ -168,6 +168,10 @@ int mbe_channel(mbe_env* env, float* out_snr, uint32_t* out_elig, void* stream);
 /* recompute the observation of the current state (after the caller edited pos / conn) */
 int mbe_observe(mbe_env* env, void* stream);
 
+/* adds this step's two-decimal QoE values (base.py:269) to acc f32 [E,4] = (sum q, sum q^2,
+ * #q < threshold, #values): the statistics of chooseBaseStation.ipynb cell 5 `qoeValue` */
+int mbe_accumulate_qoe(mbe_env* env, float* acc, float threshold, void* stream);
+
 /* number of kernel launches this handle has enqueued so far */
 int64_t mbe_launch_count(const mbe_env* env);
 

@@ -103,6 +103,7 @@ SYMBOLS = [
     ("mbe_stage", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("mbe_channel", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("mbe_observe", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("mbe_accumulate_qoe", C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     ("mbe_launch_count", C.c_int64, [C.c_void_p]),
     ("mbe_step_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 ]

@@ -446,6 +446,19 @@ int mbe_channel(mbe_env* env, float* out_snr, uint32_t* out_elig, void* stream) 
   return 0;
 }
 
+int mbe_accumulate_qoe(mbe_env* env, float* acc, float threshold, void* stream) {
+  if (!env || !acc) return fail("mbe_accumulate_qoe: null argument");
+  if (!env->bound) return fail("mbe_bind has not been called");
+  if ((uintptr_t)acc & 15) return fail("mbe_accumulate_qoe: acc must be 16-byte aligned");
+  const mbe::StepArgs& a = env->args;
+  const int per_blk = mbe::kThreads / 32;
+  mbe::qoe_accumulate_kernel<<<(a.E + per_blk - 1) / per_blk, mbe::kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      a.utility, reinterpret_cast<float4*>(acc), a.E, a.U, threshold);
+  MBE_CUDA(cudaGetLastError());
+  env->launches += 1;
+  return 0;
+}
+
 int64_t mbe_launch_count(const mbe_env* env) { return env ? env->launches : 0; }
 
 int mbe_step_host(mbe_env* env, const int32_t* actions_host, float* obs_host, float* reward_host,

@@ -396,4 +396,32 @@ __global__ void __launch_bounds__(kThreads) channel_kernel(const __grid_constant
   if (out_elig) out_elig[idx] = elig;
 }
 
+// Episode statistics of the per-UE QoE behind the fork's layout score (chooseBaseStation.ipynb
+// cell 5 `qoeValue`: mean - 0.1*var - 10*P(qoe < threshold) over all two-decimal QoE values of an
+// epoch, as stored by base.py:269).  One warp per env adds this step's U values to acc[env] =
+// (sum q, sum q^2, #q < threshold, #values); a fixed lane-strided order keeps it deterministic.
+__global__ void __launch_bounds__(kThreads) qoe_accumulate_kernel(const float* __restrict__ utility, float4* acc, int E,
+                                                                  int U, float threshold) {
+  const int env = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (env >= E) return;
+  float s1 = 0.0f, s2 = 0.0f, neg = 0.0f;
+  for (int u = lane; u < U; u += 32) {
+    float q = rintf(utility[(size_t)env * U + u] * 100.0f) * 0.01f;  // round(qoe, 2)
+    s1 += q;
+    s2 = fmaf(q, q, s2);
+    neg += (q < threshold) ? 1.0f : 0.0f;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s1 += __shfl_down_sync(kFull, s1, off);
+    s2 += __shfl_down_sync(kFull, s2, off);
+    neg += __shfl_down_sync(kFull, neg, off);
+  }
+  if (lane == 0) {
+    float4 a = acc[env];
+    acc[env] = make_float4(a.x + s1, a.y + s2, a.z + neg, a.w + (float)U);
+  }
+}
+
 }  // namespace mbe

@@ -450,6 +450,32 @@ def test_wide_connection_mask_has_two_words():
     assert env.plan.num_ues == 70 and env.conn.dim() == 3 and env.conn.shape[2] == 2
 
 
+def test_layout_scorer_matches_notebook_formula():
+    """chooseBaseStation.ipynb cell 5 `qoeValue` over the oracle's two-decimal QoE values."""
+    from mobile_env_gan_b200.scenarios import MComCustom
+    from mobile_env_gan_b200.scoring import LayoutScorer
+
+    E = 500
+    env = MComCustom(config={"num_envs": E})
+    mir = Mirror(env)
+    scorer = LayoutScorer(env)
+    env.reset(), mir.reset()
+    qoe = []
+    for k in range(20):
+        env.step(0, k)
+        scorer.update()
+        qoe.append(np.round(mir.step_fork()["utility"], 2))
+    all_qoe = np.concatenate(qoe, axis=1)  # [E, T*U]
+    want = all_qoe.mean(axis=1) - 0.1 * all_qoe.var(axis=1) - 10.0 * (all_qoe < 0.0).mean(axis=1)
+    got = scorer.result()
+    # FP32 utilities may round to the neighbouring cent in a few of the 140 values per env
+    np.testing.assert_allclose(got["Score"].cpu().numpy(), want, atol=0.08, rtol=0)
+    assert np.abs(got["Score"].cpu().numpy() - want).mean() < 2e-3
+    np.testing.assert_allclose(got["Average QoE"].cpu().numpy(), all_qoe.mean(axis=1), atol=2e-4)
+    idx, _ = scorer.best(5)
+    assert set(idx.cpu().tolist()) <= set(np.argsort(-want)[:12].tolist())
+
+
 def test_errors_are_loud():
     MComCore, BaseStation, UserEquipment = _mods()
     from mobile_env_gan_b200._lib import MbeError
