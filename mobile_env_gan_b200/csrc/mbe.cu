@@ -276,6 +276,11 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   const void* fn = gym ? (ma ? (const void*)mbe::step_kernel<1, 1> : (const void*)mbe::step_kernel<1, 0>)
                        : (const void*)mbe::step_kernel<0, 0>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem);
+  if (e == cudaSuccess && env->big) {
+    const void* bf = gym ? (ma ? (const void*)mbe::step_big_kernel<1, 1> : (const void*)mbe::step_big_kernel<1, 0>)
+                         : (const void*)mbe::step_big_kernel<0, 0>;
+    e = cudaFuncSetAttribute(bf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mbe::BigSmem));
+  }
   if (e == cudaSuccess && env->spec)
     e = cudaFuncSetAttribute((const void*)env->spec, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)env->spec_smem);
@@ -376,11 +381,11 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
       return fail("split phases / observe are not available on the block-per-env kernel (wide shapes)");
     if (a.dbg_snr || a.inj_wp) return fail("debug SNR / waypoint injection are not available for wide shapes");
     if (!gym)
-      mbe::step_big_kernel<0, 0><<<env->grid, mbe::kBigThreads, 0, st>>>(a);
+      mbe::step_big_kernel<0, 0><<<env->grid, mbe::kBigThreads, sizeof(mbe::BigSmem), st>>>(a);
     else if (!ma)
-      mbe::step_big_kernel<1, 0><<<env->grid, mbe::kBigThreads, 0, st>>>(a);
+      mbe::step_big_kernel<1, 0><<<env->grid, mbe::kBigThreads, sizeof(mbe::BigSmem), st>>>(a);
     else
-      mbe::step_big_kernel<1, 1><<<env->grid, mbe::kBigThreads, 0, st>>>(a);
+      mbe::step_big_kernel<1, 1><<<env->grid, mbe::kBigThreads, sizeof(mbe::BigSmem), st>>>(a);
     MBE_CUDA(cudaGetLastError());
     env->launches += 1;
     return 0;

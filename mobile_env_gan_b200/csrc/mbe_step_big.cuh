@@ -24,7 +24,9 @@ struct BigSmem {
   int red_i[2][kBigThreads / 32];
   float usum, rsum;
   int csum, ncon;
-  float tile[kBigThreads / 32][32][33];  // per-warp transpose tile of the observation writer
+  // per-warp rows of the observation writer: first the log2(snr) of every BS (one pass), then
+  // reused as the transpose tile of the other feature segments (odd stride: conflict-free)
+  float rows[kBigThreads / 32][32][kBigMaxB + 1];
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -56,7 +58,8 @@ template <int MODE, int HANDLER>
 __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_constant__ StepArgs a) {
   constexpr bool GYM = (MODE == 1);
   constexpr bool MA = (HANDLER == 1);
-  __shared__ BigSmem s;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BigSmem& s = *reinterpret_cast<BigSmem*>(smem_raw);
   const int U = a.U, B = a.B, F = a.F, MW = (B + 31) >> 5;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int env = blockIdx.x;
@@ -105,6 +108,8 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
     }
   }
   bool done = false, fresh = false;
+  const bool one_class = a.n_classes == 1;
+  const int d2max0 = a.cls[0].d2max;
 
   auto d2_to = [&](int i, int b) {
     int bx, by;
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
       const size_t idx = (size_t)env * U + u;
       for (int b = 0; b < nb; ++b) {
         const int d2 = d2_to(i, b);
-        if (d2 <= a.cls[s.cls[b]].d2max) {  // check_connectivity (base.py:212-214)
+        if (d2 <= (one_class ? d2max0 : a.cls[s.cls[b]].d2max)) {  // check_connectivity (base.py:212-214)
           if (b < 32) e0[i] |= 1u << b; else e1[i] |= 1u << (b - 32);
           if (!GYM && d2 < bestd2[i]) {  // nearest connectable BS, first minimum (base.py:240)
             best[i] = b;
@@ -343,59 +348,61 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
   }
 
   // ---- POST: observation rows (GYM) ----
-  // A lane owns one UE row of F floats; rows of the warp's 32 UEs are contiguous in HBM.  Features
-  // are produced 32 columns at a time into a padded shared tile and written back transposed, so
-  // every global store instruction covers 128 contiguous bytes of one row.
+  // A lane owns one UE row of F floats; the rows of the warp's 32 UEs are contiguous in HBM.  Each
+  // feature segment (connections | snr ratios | utility | broadcast utilities | broadcast counts)
+  // is produced 32 columns at a time into a padded shared tile and written back transposed, so a
+  // store instruction covers 128 contiguous bytes of one row.  log2(snr) is evaluated once per
+  // pair and parked in shared memory until the row maximum is known.
   if (GYM && touched) {
-    float (*tile)[33] = s.tile[warp];
+    float (*tile)[kBigMaxB + 1] = s.rows[warp];
 #pragma unroll
     for (int i = 0; i < kBigMaxI; ++i) {
       const int u0 = warp * 32 + i * kBigThreads;  // first UE of this warp's row group
       if (u0 >= U) continue;                        // warp-uniform
-      const int u = u0 + lane;
-      const bool live_ue = u < U;
-      const bool zero_row = done && !fresh;
-      float lmax = -INFINITY;
-      if (live_ue && !zero_row)
+      const bool active = (u0 + lane < U) && !(done && !fresh);
+      float* gbase = a.obs + ((size_t)env * U + u0) * F;
+      const int nrows = min(32, U - u0);
+      // transposed write-back of tile columns [c0, c0 + n) to feature columns [f0, f0 + n)
+      auto flush = [&](int f0, int c0_, int n) {
+        __syncwarp();
+        if (lane < n) {
+          float* g = gbase + f0 + lane;
+          for (int r = 0; r < nrows; ++r, g += F) *g = tile[r][c0_ + lane];
+        }
+        __syncwarp();
+      };
+      // pass over the BSs: log2 snr, its maximum, connectable mask, MA count total
+      float lmax = -INFINITY, tot = 0.0f;
+      uint32_t k0 = 0, k1 = 0;
+      if (active)
         for (int b = 0; b < nb; ++b) {
           const ClassDev& c = a.cls[s.cls[b]];
-          lmax = fmaxf(lmax, log2_snr_obs(c.k_hi, c.l0_hi, d2_to(i, b)));
-        }
-      float tot = 0.0f;  // MA: sum of the broadcast connection counts of the connectable BSs
-      if (MA && live_ue && !zero_row)
-        for (int b = 0; b < nb; ++b)
-          if (d2_to(i, b) <= a.cls[s.cls[b]].d2max) tot += (float)s.cnt[b];
-      const float inv_tot = 1.0f / fmaxf(1.0f, tot);
-      float* gbase = a.obs + ((size_t)env * U + u0) * F;
-      for (int f0 = 0; f0 < F; f0 += 32) {
-        for (int j = 0; j < 32; ++j) {
-          const int f = f0 + j;  // warp-uniform feature index
-          float v = 0.0f;
-          if (f < F && live_ue && !zero_row) {
-            if (f < B) {
-              v = has_bit(c0[i], c1[i], f) ? 1.0f : 0.0f;
-            } else if (f < 2 * B) {
-              const int b = f - B;
-              if (b < nb) {
-                const ClassDev& c = a.cls[s.cls[b]];
-                v = ex2_sfu(log2_snr_obs(c.k_hi, c.l0_hi, d2_to(i, b)) - lmax);  // snr / max snr
-              }
-            } else if (f == 2 * B) {
-              v = (fresh || t_e == 0) ? -1.0f : util[i];
-            } else {
-              const int b = (f - 2 * B - 1) % B;
-              const bool ok = (b < nb) && d2_to(i, b) <= a.cls[s.cls[b]].d2max;
-              if (f < 3 * B + 1) v = ok ? s.bsu[b] : -1.0f;
-              else v = ok ? (float)s.cnt[b] * inv_tot : 0.0f;
-            }
+          const int d2 = d2_to(i, b);
+          const float l = log2_snr_obs(c.k_hi, c.l0_hi, d2);
+          tile[lane][b] = l;
+          lmax = fmaxf(lmax, l);
+          if (d2 <= c.d2max) {
+            if (b < 32) k0 |= 1u << b; else k1 |= 1u << (b - 32);
+            tot += (float)s.cnt[b];
           }
-          tile[lane][j] = v;
         }
-        __syncwarp();
-        const int f = f0 + lane;
-        for (int r = 0; r < 32; ++r)
-          if (f < F && u0 + r < U) gbase[(size_t)r * F + f] = tile[r][lane];
-        __syncwarp();
+      const float inv_tot = 1.0f / fmaxf(1.0f, tot);
+      // (2) snr / max snr, in place over the parked log2 values
+      for (int b = 0; b < B; ++b) tile[lane][b] = (active && b < nb) ? ex2_sfu(tile[lane][b] - lmax) : 0.0f;
+      for (int b0 = 0; b0 < B; b0 += 32) flush(B + b0, b0, min(32, B - b0));
+      // (1) connection one-hot
+      for (int b = 0; b < B; ++b) tile[lane][b] = (active && has_bit(c0[i], c1[i], b)) ? 1.0f : 0.0f;
+      for (int b0 = 0; b0 < B; b0 += 32) flush(b0, b0, min(32, B - b0));
+      tile[lane][0] = active ? ((fresh || t_e == 0) ? -1.0f : util[i]) : 0.0f;  // (3) own utility
+      flush(2 * B, 0, 1);
+      if (MA) {
+        // (4) broadcast BS utilities
+        for (int b = 0; b < B; ++b) tile[lane][b] = active ? (has_bit(k0, k1, b) ? s.bsu[b] : -1.0f) : 0.0f;
+        for (int b0 = 0; b0 < B; b0 += 32) flush(2 * B + 1 + b0, b0, min(32, B - b0));
+        // (5) broadcast connection counts, normalised
+        for (int b = 0; b < B; ++b)
+          tile[lane][b] = (active && has_bit(k0, k1, b)) ? (float)s.cnt[b] * inv_tot : 0.0f;
+        for (int b0 = 0; b0 < B; b0 += 32) flush(3 * B + 1 + b0, b0, min(32, B - b0));
       }
     }
   }
