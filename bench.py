@@ -199,7 +199,8 @@ def main():
             envs[(start + i) % R].step(envs[(start + i) % R].actions)
 
     chunk = R * 8
-    graph = None
+    graph = graph_rem = None
+    rem = args.steps % chunk
     with torch.cuda.stream(stream):
         raw_steps(chunk)  # first touches outside the graph
         torch.cuda.synchronize()
@@ -207,12 +208,19 @@ def main():
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=stream):
                 raw_steps(chunk)
+            if rem:  # the timed region is then graph replays only, whatever K is
+                graph_rem = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph_rem, stream=stream):
+                    raw_steps(rem)
 
         def run_steps(n):
             done = 0
             while graph is not None and n - done >= chunk:
                 graph.replay()
                 done += chunk
+            if graph_rem is not None and n - done == rem:
+                graph_rem.replay()
+                done += rem
             raw_steps(n - done)
 
         # preheat (untimed) so that clocks are up, then W warm-up steps

@@ -222,15 +222,20 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
       const int u = tid + i * kBigThreads;
       if (u >= U) continue;
       const size_t idx = (size_t)env * U + u;
-      for (int b = 0; b < nb; ++b) {
-        const int d2 = d2_to(i, b);
-        if (d2 <= (one_class ? d2max0 : a.cls[s.cls[b]].d2max)) {  // check_connectivity (base.py:212-214)
-          if (b < 32) e0[i] |= 1u << b; else e1[i] |= 1u << (b - 32);
-          if (!GYM && d2 < bestd2[i]) {  // nearest connectable BS, first minimum (base.py:240)
-            best[i] = b;
-            bestd2[i] = d2;
+      for (int w = 0; w < 2; ++w) {  // one 32-bit mask word at a time (no per-BS word select)
+        uint32_t ew = 0;
+        const int b_lo = 32 * w, b_hi = min(nb, 32 * w + 32);
+        for (int b = b_lo; b < b_hi; ++b) {
+          const int d2 = d2_to(i, b);
+          if (d2 <= (one_class ? d2max0 : a.cls[s.cls[b]].d2max)) {  // check_connectivity (base.py:212-214)
+            ew |= 1u << (b - b_lo);
+            if (!GYM && d2 < bestd2[i]) {  // nearest connectable BS, first minimum (base.py:240)
+              best[i] = b;
+              bestd2[i] = d2;
+            }
           }
         }
+        if (w) e1[i] = ew; else e0[i] = ew;
       }
       if (GYM) {
         c0[i] &= e0[i];  // update_connections (base.py:221-227)
@@ -367,7 +372,9 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
         __syncwarp();
         if (lane < n) {
           float* g = gbase + f0 + lane;
-          for (int r = 0; r < nrows; ++r, g += F) *g = tile[r][c0_ + lane];
+          const float* t = &tile[0][c0_ + lane];
+#pragma unroll 8
+          for (int r = 0; r < nrows; ++r) g[(size_t)r * F] = t[r * (kBigMaxB + 1)];
         }
         __syncwarp();
       };
@@ -391,7 +398,11 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
       for (int b = 0; b < B; ++b) tile[lane][b] = (active && b < nb) ? ex2_sfu(tile[lane][b] - lmax) : 0.0f;
       for (int b0 = 0; b0 < B; b0 += 32) flush(B + b0, b0, min(32, B - b0));
       // (1) connection one-hot
-      for (int b = 0; b < B; ++b) tile[lane][b] = (active && has_bit(c0[i], c1[i], b)) ? 1.0f : 0.0f;
+      {
+        const uint32_t m0 = active ? c0[i] : 0u, m1 = active ? c1[i] : 0u;
+        for (int b = 0; b < min(B, 32); ++b) tile[lane][b] = ((m0 >> b) & 1u) ? 1.0f : 0.0f;
+        for (int b = 32; b < B; ++b) tile[lane][b] = ((m1 >> (b - 32)) & 1u) ? 1.0f : 0.0f;
+      }
       for (int b0 = 0; b0 < B; b0 += 32) flush(b0, b0, min(32, B - b0));
       tile[lane][0] = active ? ((fresh || t_e == 0) ? -1.0f : util[i]) : 0.0f;  // (3) own utility
       flush(2 * B, 0, 1);
