@@ -263,6 +263,7 @@ __device__ __forceinline__ void reinit_env(const StepArgs& a, bool sel, unsigned
       }
       if (u == 0 && a.nbs) a.nbs[env] = nb;
     }
+    if (u == 0) a.episode[env] = epi;
     fresh = true;
   }
   __syncwarp();
@@ -272,26 +273,29 @@ __device__ __forceinline__ void reinit_env(const StepArgs& a, bool sel, unsigned
 // block is whole and aligned, else a predicated cooperative copy
 __device__ __forceinline__ void store_obs_block(const StepArgs& a, const float* sobs, int env_base, int tid,
                                                 bool whole) {
-  const int envs_here = min(a.epb, a.E - env_base);
-  const size_t words = (size_t)envs_here * a.U * a.F;
-  float* gdst = a.obs + (size_t)env_base * a.U * a.F;
-  if (whole && a.obs_bulk_ok && (words % 4 == 0)) {
+  // fast path: a full block (epb*U*F*4 bytes is a multiple of 16 by construction) leaves as one
+  // bulk copy issued by thread 0; nobody else computes an address
+  if (whole && a.obs_bulk_ok && env_base + a.epb <= a.E) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
+      const uint32_t bytes = (uint32_t)(a.epb * a.U * a.F) * 4u;
+      float* gdst = a.obs + (size_t)env_base * (size_t)(a.U * a.F);
       uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sobs);
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr),
-                   "r"((uint32_t)(words * 4))
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes)
                    : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
-  } else {
-    __syncthreads();
-    for (size_t i = tid; i < words; i += kThreads) {
-      int e = env_base + (int)(i / ((size_t)a.U * a.F));
-      if (whole || a.reset_mask[e] != 0) gdst[i] = sobs[i];
-    }
+    return;
+  }
+  const int envs_here = min(a.epb, a.E - env_base);
+  const size_t words = (size_t)envs_here * a.U * a.F;
+  float* gdst = a.obs + (size_t)env_base * a.U * a.F;
+  __syncthreads();
+  for (size_t i = tid; i < words; i += kThreads) {
+    int e = env_base + (int)(i / ((size_t)a.U * a.F));
+    if (whole || a.reset_mask[e] != 0) gdst[i] = sobs[i];
   }
 }
 

@@ -344,7 +344,6 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     if (GYM && (conn != conn_in || op == OP_RESET)) a.conn[idx] = conn;
     if (u == 0) {
       if ((ph & 4) || op == OP_RESET) a.t[env] = t_e;
-      if (fresh) a.episode[env] = epi;
     }
   }
 

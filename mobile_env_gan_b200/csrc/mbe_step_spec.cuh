@@ -325,7 +325,6 @@ __device__ __forceinline__ void step_chunk(const StepArgs& a, const int env_base
     if (GYM && conn != conn_in) a.conn[idx] = conn;
     if (u == 0) {
       a.t[env] = t_e;
-      if (fresh) a.episode[env] = epi;
     }
   }
 }
