@@ -1,0 +1,210 @@
+"""More GPU coverage: random shapes on the generic kernel, partial resets, observe(), state
+round trips, Monitor, multi-agent 1M-env sharding slice, NCCL stats gather (needs 2 GPUs)."""
+import os
+
+import numpy as np
+import pytest
+
+from mirror import Mirror, conn_bits
+from test_gpu_parity import ATOL, RTOL, close, make_env
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_shapes_generic_kernel(seed):
+    """Shapes without a specialisation (any U, B <= 32, several BS classes) against the oracle."""
+    rng = np.random.default_rng(100 + seed)
+    U, B = int(rng.integers(1, 33)), int(rng.integers(1, 33))
+    E = int(rng.integers(33, 400))
+    handler = "ma" if seed % 2 else "central"
+    bs = rng.integers(0, 200, size=(B, 2)).tolist()
+    cfg = {"num_envs": E, "mode": "gym", "handler": handler, "autoreset": bool(seed % 3 == 0),
+           "EP_MAX_TIME": 6, "arrival_params": {"ep_time": 6}, "ue": {"velocity": float(rng.choice([1.5, 4, 10, 12.5]))},
+           "seed": int(rng.integers(0, 10**6)), "movement_params": {"reset_rng_episode": bool(seed % 2)}}
+    env = make_env(bs, U, cfg)
+    mir = Mirror(env)
+    obs, _ = env.reset()
+    close(obs.cpu().numpy().reshape(E, U, -1), mir.reset(), "reset obs")
+    for k in range(14):
+        acts = rng.integers(0, B + 1, size=(E, U)).astype(np.int32)
+        obs, rew, _, trunc, _ = env.step(torch.from_numpy(acts).to(env.device))
+        out = mir.step_gym(acts)
+        assert np.array_equal(env.conn.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, conn_bits(out["conn_after"])), k
+        assert np.array_equal(env.pos.cpu().numpy(), out["pos_after"]), k
+        assert np.array_equal(env.rate.cpu().numpy(), out["rate"]), k
+        close(rew.cpu(), out["reward"], f"reward {k}")
+        close(obs.cpu().numpy().reshape(E, U, -1), out["obs"], f"obs {k}")
+        if not cfg["autoreset"] and out["done"].all():
+            break
+
+
+def test_two_bs_classes_run_on_generic_kernel_and_match_oracle_per_class():
+    """BSs with different radio parameters: class-specific cut-off distance and rate table."""
+    from mobile_env_gan_b200.core.base import MComCore
+    from mobile_env_gan_b200.core.entities import BaseStation, UserEquipment
+    from mobile_env_gan_b200.core.util import deep_dict_merge
+    from oracle import mbe_oracle as orc
+
+    config = {"num_envs": 64, "mode": "fork", "ue": {"velocity": 8}}
+    cfg = deep_dict_merge(MComCore.default_config(), config)
+    stations = [BaseStation(0, (60, 60), **cfg["bs"]), BaseStation(1, (140, 140), **dict(cfg["bs"], tx=30))]
+    users = [UserEquipment(i, **cfg["ue"]) for i in range(9)]
+    env = MComCore(stations, users, config)
+    assert len(env.plan.classes) == 2
+    env.reset()
+    p_hi, p_lo = orc.Params(velocity=8), orc.Params(velocity=8, tx=30)
+    for k in range(10):
+        env.step(0, k)
+        pos = env.pos.cpu().numpy().astype(np.int64)
+        snr_hi, d2 = orc.batch_snr(p_hi, pos, np.array([[60, 60], [140, 140]]))
+        snr_lo, _ = orc.batch_snr(p_lo, pos, np.array([[60, 60], [140, 140]]))
+        snr = np.stack([snr_hi[:, :, 0], snr_lo[:, :, 1]], axis=2)
+        assoc, _ = orc.batch_assoc_fork(p_hi, snr, d2)
+        assert np.array_equal(env.assoc.cpu().numpy(), assoc), k
+        conn = assoc[:, :, None] == np.arange(2)[None, None, :]
+        n = conn.sum(axis=1, keepdims=True)
+        raw = 9e6 * np.log2(1 + snr)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            want = np.round(np.where(conn, raw / n, 0.0), 2).sum(axis=2)
+        assert np.array_equal(env.rate.cpu().numpy(), want), k
+
+
+def test_partial_reset_and_observe():
+    bs, U = [(50, 50), (150, 50), (50, 150), (150, 150)], 15
+    E = 200
+    env = make_env(bs, U, {"num_envs": E, "mode": "gym", "handler": "ma", "ue": {"velocity": 5},
+                           "movement_params": {"reset_rng_episode": False}})
+    mir = Mirror(env)
+    env.reset(), mir.reset()
+    rng = np.random.default_rng(2)
+    for k in range(5):
+        acts = rng.integers(0, 5, size=(E, U)).astype(np.int32)
+        obs, *_ = env.step(torch.from_numpy(acts).cuda())
+        out = mir.step_gym(acts)
+    mask = rng.random(E) < 0.3
+    before = {n: getattr(env, n).clone() for n in ("pos", "wp", "conn", "t", "episode", "obs", "utility_scaled")}
+    obs, _ = env.reset(env_mask=torch.from_numpy(mask).cuda())
+    fresh = mir.reset(mask)
+    sel = torch.from_numpy(mask).cuda()
+    for n, old in before.items():  # unselected envs are untouched, bit for bit
+        assert torch.equal(getattr(env, n)[~sel], old[~sel]), n
+    assert np.array_equal(env.pos.cpu().numpy(), mir.pos)
+    assert np.array_equal(env.t.cpu().numpy(), mir.t) and np.array_equal(env.episode.cpu().numpy(), mir.episode)
+    close(obs.cpu().numpy()[mask], fresh[mask], "obs of the re-initialised envs")
+    # keep stepping: both populations continue correctly
+    for k in range(4):
+        acts = rng.integers(0, 5, size=(E, U)).astype(np.int32)
+        obs, rew, *_ = env.step(torch.from_numpy(acts).cuda())
+        out = mir.step_gym(acts)
+        assert np.array_equal(env.pos.cpu().numpy(), out["pos_after"])
+        close(obs.cpu().numpy(), out["obs"], f"obs {k}")
+    # observe() recomputes the observation of an edited state
+    env.set_positions(np.broadcast_to(np.array([50, 50]), (E, U, 2)).copy())
+    o = env.observe().cpu().numpy()
+    assert np.allclose(o[:, :, 4], 1.0)  # standing on BS 0: its snr ratio is the maximum
+
+
+def test_state_dict_replay_is_bit_identical():
+    import mobile_env_gan_b200 as mbe
+
+    env = mbe.make("mobile-medium-ma-v0", num_envs=1024, autoreset=True)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    acts = [torch.randint(0, 5, (1024, 15), generator=g, device="cuda", dtype=torch.int32) for _ in range(30)]
+    for a in acts[:10]:
+        env.step(a)
+    snap = env.state_dict()
+    first = []
+    for a in acts[10:]:
+        obs, rew, *_ = env.step(a)
+        first.append((obs.clone(), rew.clone()))
+    env.load_state_dict(snap)
+    for a, (o, r) in zip(acts[10:], first):
+        obs, rew, *_ = env.step(a)
+        assert torch.equal(obs, o) and torch.equal(rew, r)
+
+
+def test_monitor_collects_device_metrics():
+    import mobile_env_gan_b200 as mbe
+
+    env = mbe.make("mobile-custom-v0", num_envs=32)
+    env.reset()
+    for k in range(5):
+        env.step(0, k)
+        env.monitor.update(env)
+    info = env.monitor.info(env=3)
+    assert set(info) >= {"number connections", "number connected", "mean utility", "mean datarate"}
+    scalar, _, _ = env.monitor.load_results(env=3)
+    assert len(scalar) == 5 and list(scalar.columns)[:2] == ["number connections", "number connected"]
+    assert scalar["number connected"].iloc[-1] == float(env.metrics[3, 1])
+    v = env.view(3)
+    assert len(v.userDict) == 7 and v.time == 5.0
+    assert sum(len(s) for s in v.bs2ue_connections.values()) == int(env.metrics[3, 0])
+
+
+def test_ma_million_env_slice_is_offset_invariant():
+    """BASELINE configs[2]: 1M envs sharded 131,072 per GPU.  A slice computed as rank 5 of 8 equals
+    the same global envs computed inside a differently placed shard."""
+    import mobile_env_gan_b200 as mbe
+    from mobile_env_gan_b200.sharding import shard_envs
+
+    off, cnt = shard_envs(1 << 20, 5, 8)
+    assert (off, cnt) == (5 * 131072, 131072)
+    n = 4096
+    a = mbe.make("mobile-medium-ma-v0", num_envs=n, env_offset=off + 1000, autoreset=True)
+    b = mbe.make("mobile-medium-ma-v0", num_envs=n + 1000, env_offset=off, autoreset=True)
+    a.reset(), b.reset()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for k in range(22):
+        acts = torch.randint(0, 5, (n + 1000, 15), generator=g, device="cuda", dtype=torch.int32)
+        oa, ra, *_ = a.step(acts[1000:])
+        ob, rb, *_ = b.step(acts)
+        assert torch.equal(oa, ob[1000:]) and torch.equal(ra, rb[1000:])
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    import mobile_env_gan_b200 as mbe
+    from mobile_env_gan_b200.sharding import gather_episode_stats, sharded_config
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    total = 1000
+    cfg = sharded_config(total)
+    env = mbe.make("mobile-custom-v0", device=f"cuda:{rank}", **cfg)
+    env.reset()
+    for k in range(3):
+        env.step(0, k)
+    full = gather_episode_stats(env.metrics, total)
+    q.put((rank, cfg["env_offset"], full.cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_nccl_stats_gather_matches_single_gpu():
+    import torch.multiprocessing as mp
+
+    import mobile_env_gan_b200 as mbe
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 200
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref = mbe.make("mobile-custom-v0", num_envs=1000)
+    ref.reset()
+    for k in range(3):
+        ref.step(0, k)
+    want = ref.metrics.cpu().numpy()
+    for _, _, full in got:
+        assert np.array_equal(full, want)  # sharding does not change any env's result
