@@ -87,9 +87,9 @@ def test_scalar_and_batch_oracles_agree_fork(seed, U, B, v, sched):
 def test_log_distance_channel_folds_like_its_formula():
     bs = BaseStation(0, (0, 0), 9e6, 2500, 40, 50)
     ue = UserEquipment(0, 1.5, 2e-8, 1e-9, 1.6)
-    ch = LogDistance(a=80.0, c=35.0)
+    ch = LogDistance(a=125.0, c=40.0)
     f = ch.fold(bs, ue, 80000)
     d = math.sqrt(f["d2max"])
-    assert 10 ** ((40 - (80 + 35 * math.log10(d))) / 10) / 1e-9 > 2e-8
+    assert 10 ** ((40 - (125 + 40 * math.log10(d))) / 10) / 1e-9 > 2e-8
     d = math.sqrt(f["d2max"] + 1)
-    assert not (10 ** ((40 - (80 + 35 * math.log10(d))) / 10) / 1e-9 > 2e-8)
+    assert not (10 ** ((40 - (125 + 40 * math.log10(d))) / 10) / 1e-9 > 2e-8)
