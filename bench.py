@@ -32,7 +32,15 @@ if ROOT not in sys.path:
 
 METRIC = "env-steps/sec (batched, whole box) for mobile-medium at 1/2/4/8 B200"
 UNIT = "env-steps/s"
-SIZES = {"mobile-small": (3, 5), "mobile-medium": (4, 15), "mobile-large": (13, 30), "mobile-synthetic": (64, 512)}
+SIZES = {"mobile-small": (3, 5), "mobile-medium": (4, 15), "mobile-large": (13, 30), "mobile-synthetic": (64, 512),
+         "mobile-custom": (10, 7)}  # custom = the fork's MComCustom (FORK mode, 5..10 random BSs per env)
+
+
+def bytes_per_env_step_fork(U: int, B: int) -> dict:
+    """FORK step (MComCustom): pos r+w 8, waypoint r 4, assoc w 4, rate f64 w 8, utility w 4 per UE;
+    per env: BS table 4B r, nbs 4, clock r+w 8, episode 4, done 1, metrics 16."""
+    ours = U * (8 + 4 + 4 + 8 + 4) + 4 * B + 4 + 8 + 4 + 1 + 16
+    return {"layout": ours, "survey_8d": U * (32 + 4) + 8 * B + 13}
 
 
 def bytes_per_env_step(U: int, B: int, handler: str) -> dict:
@@ -176,10 +184,14 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    size, handler = args.workload.rsplit("-", 2)[0], args.workload.split("-")[2]
+    fork = args.workload == "mobile-custom-v0"
+    if fork:
+        size, handler = "mobile-custom", "fork"
+    else:
+        size, handler = args.workload.rsplit("-", 2)[0], args.workload.split("-")[2]
     B, U = SIZES[size]
     E = args.envs
-    bpe = bytes_per_env_step(U, B, handler)
+    bpe = bytes_per_env_step_fork(U, B) if fork else bytes_per_env_step(U, B, handler)
     # rotate over R independent batches so that each step's inputs/outputs are not L2-resident
     footprint = E * bpe["layout"]
     R = max(2, -(-int(2.2 * 126e6) // footprint))
@@ -191,12 +203,17 @@ def main():
         envs.append(env)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     for env in envs:  # synthetic policy output: uniform actions in [0, B]
-        env.actions.copy_(torch.randint(0, B + 1, (E, U), generator=g, device=dev, dtype=torch.int32))
+        if not fork:
+            env.actions.copy_(torch.randint(0, B + 1, (E, U), generator=g, device=dev, dtype=torch.int32))
     stream = torch.cuda.Stream(device=dev)
 
     def raw_steps(n, start=0):
         for i in range(n):
-            envs[(start + i) % R].step(envs[(start + i) % R].actions)
+            env = envs[(start + i) % R]
+            if fork:
+                env.step(0, i)
+            else:
+                env.step(env.actions)
 
     chunk = R * 8
     graph = graph_rem = None
@@ -254,23 +271,46 @@ def main():
 
         # ---- end to end through the host-buffer ABI call ----
         e2e_steps = max(5, min(args.steps, 40))
-        F = envs[0].plan.feature_size
-        acts_h = [torch.randint(0, B + 1, (E, U), dtype=torch.int32).pin_memory() for _ in range(2)]
-        obs_h = torch.empty(E, U * F, dtype=torch.float32).pin_memory()
-        rew_h = torch.empty(E, dtype=torch.float32).pin_memory() if handler == "central" else \
-            torch.empty(E, U, dtype=torch.float32).pin_memory()
-        done_h = torch.empty(E, dtype=torch.uint8).pin_memory()
+        if fork:
+            # the reference's step returns None; its caller reads positions, association, rates and
+            # QoE from the env afterwards (base.py:264-269): step + those tensors to pinned host memory
+            names = ("pos", "assoc", "rate", "utility_scaled", "metrics", "done")
+            host = {n: torch.empty_like(getattr(envs[0], n), device="cpu").pin_memory() for n in names}
+            h2d, d2h = 0, sum(t.numel() * t.element_size() for t in host.values())
+
+            def e2e_step(i):
+                env = envs[i % R]
+                env.step(0, i)
+                for n in names:
+                    host[n].copy_(getattr(env, n), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+            api = "MComCustom.step + D2H of pos/assoc/rate/utility/metrics/done"
+        else:
+            F = envs[0].plan.feature_size
+            acts_h = [torch.randint(0, B + 1, (E, U), dtype=torch.int32).pin_memory() for _ in range(2)]
+            obs_h = torch.empty(E, U * F, dtype=torch.float32).pin_memory()
+            rew_h = torch.empty(E, dtype=torch.float32).pin_memory() if handler == "central" else \
+                torch.empty(E, U, dtype=torch.float32).pin_memory()
+            done_h = torch.empty(E, dtype=torch.uint8).pin_memory()
+            h2d = E * U * 4
+            d2h = E * U * F * 4 + rew_h.numel() * 4 + E
+
+            def e2e_step(i):
+                envs[i % R].step_host(acts_h[i % 2], obs_h, rew_h, done_h)
+
+            api = "mbe_step_host (pinned host buffers)"
         for i in range(3):
-            envs[i % R].step_host(acts_h[i % 2], obs_h, rew_h, done_h)
+            e2e_step(i)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            envs[i % R].step_host(acts_h[i % 2], obs_h, rew_h, done_h)
+            e2e_step(i)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-        checksum = float(rew_h.sum())
+        checksum = float(host["utility_scaled"].sum()) if fork else float(rew_h.sum())
 
     times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -281,27 +321,26 @@ def main():
         per_launch_s = ms * 1e-3 / args.steps
         achieved = bpe["layout"] * E / per_launch_s / 1e9
         value = world * E * args.steps / (ms * 1e-3)
-        h2d = E * U * 4
-        d2h = E * U * F * 4 + rew_h.numel() * 4 + E
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": args.workload, "envs_per_gpu": E, "bs": B, "ues": U,
-                "actions": "uniform int32 in [0,B], resident in HBM", "autoreset": True, "ep_time": 20,
+                "actions": "none (FORK step)" if fork else "uniform int32 in [0,B], resident in HBM",
+                "autoreset": True, "ep_time": 20,
                 "l2": f"rotating {R} independent env batches, {R * footprint / 1e6:.0f} MB > 126 MB L2",
                 "launch": "CUDA graph replay" if graph is not None else "stream launches",
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "kernel": (f"mbe::step_spec_kernel<gym,{handler},U={U},B={B}>" if U <= 32 and B <= 32 else f"mbe::step_big_kernel<gym,{handler}> U={U} B={B}"),
+                "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "kernel": (f"mbe::step_spec_kernel<{'fork' if fork else 'gym'},{handler},U={U},B={B}>" if U <= 32 and B <= 32 else f"mbe::step_big_kernel<gym,{handler}> U={U} B={B}"),
                 "bytes_per_env_step": bpe["layout"], "bytes_per_env_step_survey_8d": bpe["survey_8d"],
                 "frac_survey_8d": bpe["survey_8d"] * E / per_launch_s / 1e9 / peak,
             },
             "cpu_baseline": cpu,
             "e2e": {"value": world * E * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "mbe_step_host (pinned host buffers)",
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": api,
                     "checksum": checksum},
             "gpu_launches": gpu_launches,
             "clocks": sampler.result(),

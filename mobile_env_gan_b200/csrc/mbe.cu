@@ -51,7 +51,6 @@ struct mbe_env {
   // specialised fused kernel for this shape (nullptr: generic kernel only)
   void (*spec)(mbe::StepArgs) = nullptr;
   size_t spec_smem = 0;
-  int spec_grid = 0;
   void (*pipe)(mbe::StepArgs) = nullptr;
   size_t pipe_smem = 0;
   int pipe_grid = 0;

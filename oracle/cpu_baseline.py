@@ -21,6 +21,8 @@ WORKLOADS = {
     "mobile-large-central-v0": (
         [(20 + 45 * (i % 4) + (22 if (i // 4) % 2 else 0), 25 + 50 * (i // 4)) for i in range(13)],
         30, "gym", "central", 1.5),
+    # the fork's own scenario (custom.py): 7 UEs at velocity 10, 5..10 random BSs per episode, FORK step
+    "mobile-custom-v0": (None, 7, "fork", "central", 10),
 }
 
 
@@ -29,13 +31,17 @@ def _worker(args):
     bs, U, mode, handler, vel = WORKLOADS[workload]
     p = orc.Params(velocity=vel)
     rng = np.random.default_rng(seed)
-    env = orc.ScalarEnv(p, bs, U, wp_source=lambda u, k: (int(rng.uniform(0, p.width)), int(rng.uniform(0, p.height))))
+    random_layout = bs is None
+    env = orc.ScalarEnv(p, bs or [(0, 0)], U,
+                        wp_source=lambda u, k: (int(rng.uniform(0, p.width)), int(rng.uniform(0, p.height))))
 
     def fresh():
+        if random_layout:  # generate_base_stations (custom.py:68-77)
+            env.bs_xy = [(int(rng.uniform(0, 200)), int(rng.uniform(0, 200))) for _ in range(int(rng.integers(5, 11)))]
         env.reset([(int(rng.uniform(0, p.width)), int(rng.uniform(0, p.height))) for _ in range(U)])
 
     fresh()
-    B = len(bs)
+    B = len(env.bs_xy)
     steps = 0
     t0 = time.perf_counter()
     while True:
