@@ -13,6 +13,14 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the C-ABI library is built in-tree (git-ignored): make sure it exists / is current before any
+    # test loads it (nvcc cross-compiles sm_100a without a GPU; on the GPU box the built file travels)
+    try:
+        from mobile_env_gan_b200.csrc.build import build
+
+        build(force=False)
+    except Exception as exc:  # no nvcc: the tests that need the library will say so
+        print(f"[conftest] libmbe.so not rebuilt: {exc}")
 
 
 def golden_names():
