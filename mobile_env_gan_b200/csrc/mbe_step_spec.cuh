@@ -9,11 +9,15 @@
 #pragma once
 #include "mbe_device.cuh"
 
-// Resident CTAs per SM the register allocation is held to: the small shapes run at full
-// occupancy (16 x 128 threads, 32 registers), measured best on B200 (profiles/README.md);
-// the wide shapes keep 64 registers for their per-BS arrays.
+// Resident CTAs (128 threads) per SM the register allocation is held to, tuned per kernel on B200
+// (profiles/README.md): the small central shapes run best at full occupancy with 32 registers, the
+// multi-agent and wide shapes need more registers for their per-BS arrays.
 #ifndef MBE_SPEC_MIN_BLOCKS
-#define MBE_SPEC_MIN_BLOCKS(B) ((B) <= 4 ? 16 : 8)
+#define MBE_SPEC_MIN_BLOCKS(MODE, HANDLER, B) \
+  ((B) <= 4 ? ((HANDLER) == 1 ? 12 : 16) : (B) <= 10 ? ((MODE) == 0 ? 11 : 10) : ((HANDLER) == 1 ? MBE_LARGE_MA_BLOCKS : 10))
+#endif
+#ifndef MBE_LARGE_MA_BLOCKS
+#define MBE_LARGE_MA_BLOCKS 8
 #endif
 
 namespace mbe {
@@ -331,7 +335,7 @@ __device__ __forceinline__ void step_chunk(const StepArgs& a, const int env_base
 
 // ---- one chunk per CTA (works for any E; also the fallback of the pipelined kernel) ----
 template <int MODE, int HANDLER, int U, int B, bool PER_ENV>
-__global__ void __launch_bounds__(kThreads, MBE_SPEC_MIN_BLOCKS(B)) step_spec_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kThreads, MBE_SPEC_MIN_BLOCKS(MODE, HANDLER, B)) step_spec_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool GYM = (MODE == 1);
   constexpr bool MA = (HANDLER == 1);
@@ -410,7 +414,7 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t
 }
 
 template <int MODE, int HANDLER, int U, int B, bool PER_ENV>
-__global__ void __launch_bounds__(kThreads, MBE_SPEC_MIN_BLOCKS(B)) step_pipe_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kThreads, MBE_SPEC_MIN_BLOCKS(MODE, HANDLER, B)) step_pipe_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool GYM = (MODE == 1);
   constexpr bool MA = (HANDLER == 1);
