@@ -144,7 +144,7 @@ class MComCore:
         if not (0 < width <= MAX_COORD and 0 < height <= MAX_COORD):
             raise ValueError("map does not fit int16 coordinates")
         mode = {"fork": _lib.MODE_FORK, "gym": _lib.MODE_GYM}[config["mode"]]
-        handler = {"central": _lib.HANDLER_CENTRAL, "ma": _lib.HANDLER_MA}[config.get("handler") or "central"]
+        handler = cls._handler_class(config).kernel_id
         bs_random = config.get("bs_random")
         max_d2 = int(width) ** 2 + int(height) ** 2 + 2
         if bs_random:
@@ -184,6 +184,18 @@ class MComCore:
         )
 
     @staticmethod
+    def _handler_class(config):
+        """config["handler"]: "central" | "ma" or a handler class (upstream passes the class)."""
+        from ..handlers import HANDLERS
+
+        h = config.get("handler") or "central"
+        if isinstance(h, str):
+            return HANDLERS[h]
+        if getattr(h, "kernel_id", None) in (0, 1):
+            return h
+        raise NotImplementedError(f"handler {h!r} has no CUDA kernel (central / multi-agent only)")
+
+    @staticmethod
     def _instantiate_plugins(config):
         return (
             config["arrival"](**config["arrival_params"]),
@@ -218,6 +230,11 @@ class MComCore:
         self.NUM_STATIONS = self.plan.num_bs
         self.num_envs = self.plan.num_envs
         self.mode = config["mode"]
+        # Gymnasium-shaped surface (vector-env naming): spaces of ONE env; the batch adds axis 0
+        self.handler = self._handler_class(config)
+        if self.plan.mode == _lib.MODE_GYM:
+            self.single_action_space = self.action_space = self.handler.action_space(self)
+            self.single_observation_space = self.observation_space = self.handler.observation_space(self)
 
         config["metrics"]["scalar_metrics"].update(
             {

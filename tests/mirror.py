@@ -26,7 +26,7 @@ class Mirror:
         self.E, self.U, self.B = pl.num_envs, pl.num_ues, pl.num_bs
         self.seed, self.off = pl.seed, pl.env_offset
         self.gym = env.config["mode"] == "gym"
-        self.handler = env.config.get("handler") or "central"
+        self.handler = "ma" if pl.handler == 1 else "central"
         self.autoreset = pl.autoreset
         self.rre = pl.reset_rng_episode
         self.bs_random = pl.bs_random if pl.bs_random[1] > 0 else None

@@ -110,6 +110,10 @@ def test_state_dict_replay_is_bit_identical():
     import mobile_env_gan_b200 as mbe
 
     env = mbe.make("mobile-medium-ma-v0", num_envs=1024, autoreset=True)
+    assert len(env.action_space.spaces) == 15 and env.observation_space.spaces[0].shape == (17,)
+    central = mbe.make("mobile-large-central-v0", num_envs=8)
+    assert central.action_space.shape == (30,) and central.observation_space.shape == (30 * 27,)
+    assert central.reset()[0].shape == (8, 30 * 27)
     env.reset()
     g = torch.Generator(device="cuda").manual_seed(0)
     acts = [torch.randint(0, 5, (1024, 15), generator=g, device="cuda", dtype=torch.int32) for _ in range(30)]

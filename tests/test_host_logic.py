@@ -191,3 +191,21 @@ def test_gloo_two_ranks_shard_and_gather():
     assert offsets == [0, 6]
     for _, _, full in got:
         assert full == want
+
+
+def test_handler_spaces_without_a_gpu():
+    """Spaces only depend on the scenario sizes (upstream shapes: MultiDiscrete([B+1]*U), Box(U*(2B+1)))."""
+    from mobile_env_gan_b200.handlers import MComCentralHandler, MComMAHandler
+
+    class Sizes:
+        NUM_STATIONS, NUM_USERS, userDict = 4, 15, {i: None for i in range(15)}
+
+    a = MComCentralHandler.action_space(Sizes)
+    o = MComCentralHandler.observation_space(Sizes)
+    assert a.shape == (15,) and int(a.nvec[0]) == 5 and o.shape == (15 * 9,)
+    am, om = MComMAHandler.action_space(Sizes), MComMAHandler.observation_space(Sizes)
+    assert len(am.spaces) == 15 and am.spaces[0].n == 5 and om.spaces[3].shape == (17,)
+    cfg = MComCore.seeding(deep_dict_merge(MComCore.default_config(), {"mode": "gym", "handler": MComMAHandler}))
+    stations = [BaseStation(0, (1, 1), **cfg["bs"])]
+    users = [UserEquipment(0, **cfg["ue"])]
+    assert MComCore.build_plan(stations, users, cfg).handler == _lib.HANDLER_MA
