@@ -228,7 +228,7 @@ def main():
             else:
                 env.step(env.actions)
 
-    chunk = R * 8
+    chunk = R * 32
     graph = graph_rem = None
     rem = args.steps % chunk
     with torch.cuda.stream(stream):
