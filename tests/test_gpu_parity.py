@@ -221,10 +221,10 @@ def test_split_phases_equal_fused_step(mode):
     ("large", "gym", "central"), ("large", "gym", "ma"), ("small", "fork", "central"),
     ("medium", "fork", "central"), ("large", "fork", "central"), ("custom", "fork", "central"),
     ("custom", "gym", "ma")])
-def test_specialised_kernels_equal_generic(scen, mode, handler):
-    """The shape-specialised fused kernels and the generic kernel share their arithmetic:
-    every output tensor must be identical, bit for bit."""
-    E = 1003
+@pytest.mark.parametrize("E", [1003, 1024])
+def test_specialised_kernels_equal_generic(scen, mode, handler, E):
+    """The shape-specialised fused kernels (warp-segment; thread-per-env when E % 32 == 0) and the
+    generic kernel share their arithmetic: every output tensor must be identical, bit for bit."""
     cfg = {"num_envs": E, "mode": mode, "handler": handler, "autoreset": True, "ue": {"velocity": 1.5},
            "EP_MAX_TIME": 9, "arrival_params": {"ep_time": 9}, "movement_params": {"reset_rng_episode": False}}
     if scen == "custom":
