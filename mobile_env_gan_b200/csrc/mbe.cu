@@ -15,6 +15,7 @@
 #include "mbe_step.cuh"
 #include "mbe_step_spec.cuh"
 #include "mbe_step_big.cuh"
+#include "mbe_step_upt.cuh"
 
 namespace {
 
@@ -55,6 +56,10 @@ struct mbe_env {
   size_t pipe_smem = 0;
   int pipe_grid = 0;
   bool big = false;  // block-per-env kernel (wide shapes, ProportionalFair)
+  // several-UEs-per-thread kernel (GYM scenario shapes, shared layout)
+  void (*upt)(mbe::StepArgs) = nullptr;
+  size_t upt_smem = 0;
+  int upt_epb = 0;
 };
 
 namespace {
@@ -77,6 +82,18 @@ struct SpecEntry {
 
 // shapes with a compile-time specialisation: the scenario sizes of BASELINE.json (small 3x5,
 // medium 4x15, large 13x30) and the fork's MComCustom (7 UEs, <= 10 random BSs per env)
+struct UptEntry {
+  int handler, U, B, K;
+  void (*fn)(mbe::StepArgs);
+  size_t smem;
+};
+#define MBE_UPT(HANDLER, U, B, K) \
+  UptEntry { HANDLER, U, B, K, mbe::step_upt_kernel<HANDLER, U, B, K>, mbe::upt_smem_bytes<HANDLER, U, B, K>() }
+#ifndef MBE_UPT_K_MEDIUM
+#define MBE_UPT_K_MEDIUM 5
+#endif
+const UptEntry kUpts[] = {MBE_UPT(0, 15, 4, MBE_UPT_K_MEDIUM), MBE_UPT(1, 15, 4, MBE_UPT_K_MEDIUM)};
+
 const SpecEntry kSpecs[] = {
     MBE_SPEC(1, 0, 5, 3, 0),  MBE_SPEC(1, 1, 5, 3, 0),  MBE_SPEC(1, 0, 15, 4, 0),  MBE_SPEC(1, 1, 15, 4, 0),
     MBE_SPEC(1, 0, 30, 13, 0), MBE_SPEC(1, 1, 30, 13, 0), MBE_SPEC(0, 0, 7, 10, 1), MBE_SPEC(0, 0, 5, 3, 0),
@@ -265,6 +282,17 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
         break;
       }
   }
+  {
+    const char* v = std::getenv("MBE_UPT");
+    const bool on = !(v && v[0] == '0');
+    if (on && spec_ok && gym && !a.bs_per_env && !env->big && !(cfg->flags & MBE_FLAG_GENERIC_KERNEL))
+      for (const UptEntry& t : kUpts)
+        if (t.handler == cfg->handler && t.U == a.U && t.B == a.B) {
+          env->upt = t.fn;
+          env->upt_smem = t.smem;
+          env->upt_epb = (32 / t.K) * MBE_UPT_WARPS;
+        }
+  }
   env->smem = env->big ? 0 : mbe::smem_bytes(gym, ma, a.epb, a.U, a.B, a.F, a.bs_per_env);
   env->grid = env->big ? a.E : (a.E + a.epb - 1) / a.epb;
   if (env->big) env->spec = nullptr;
@@ -283,6 +311,8 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   if (e == cudaSuccess && env->spec)
     e = cudaFuncSetAttribute((const void*)env->spec, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)env->spec_smem);
+  if (e == cudaSuccess && env->upt)
+    e = cudaFuncSetAttribute((const void*)env->upt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->upt_smem);
   if (e == cudaSuccess && env->pipe) {
     // measured slower than the one-chunk-per-CTA kernel on B200 (profiles/README.md): opt-in only
     const char* v = std::getenv("MBE_PIPE");
@@ -386,6 +416,22 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
     else
       mbe::step_big_kernel<1, 1><<<env->grid, mbe::kBigThreads, sizeof(mbe::BigSmem), st>>>(a);
     MBE_CUDA(cudaGetLastError());
+    env->launches += 1;
+    return 0;
+  }
+  if (env->upt && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr && !a.inj_wp) {
+    a.epb = env->upt_epb;  // envs per CTA of this mapping (bounds and size of the obs bulk store)
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((a.E + a.epb - 1) / a.epb);
+    lc.blockDim = dim3(32 * MBE_UPT_WARPS);
+    lc.dynamicSmemBytes = env->upt_smem;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    MBE_CUDA(cudaLaunchKernelEx(&lc, env->upt, a));
     env->launches += 1;
     return 0;
   }

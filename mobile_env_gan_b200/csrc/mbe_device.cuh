@@ -271,6 +271,7 @@ __device__ __forceinline__ void reinit_env(const StepArgs& a, bool sel, unsigned
 
 // the observation block of a CTA leaves shared memory: one bulk async copy (TMA) when the
 // block is whole and aligned, else a predicated cooperative copy
+template <int THREADS = kThreads>
 __device__ __forceinline__ void store_obs_block(const StepArgs& a, const float* sobs, int env_base, int tid,
                                                 bool whole) {
   // fast path: a full block (epb*U*F*4 bytes is a multiple of 16 by construction) leaves as one
@@ -293,7 +294,7 @@ __device__ __forceinline__ void store_obs_block(const StepArgs& a, const float* 
   const size_t words = (size_t)envs_here * a.U * a.F;
   float* gdst = a.obs + (size_t)env_base * a.U * a.F;
   __syncthreads();
-  for (size_t i = tid; i < words; i += kThreads) {
+  for (size_t i = tid; i < words; i += THREADS) {
     int e = env_base + (int)(i / ((size_t)a.U * a.F));
     if (whole || a.reset_mask[e] != 0) gdst[i] = sobs[i];
   }

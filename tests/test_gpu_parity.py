@@ -211,7 +211,11 @@ def test_split_phases_equal_fused_step(mode):
             b.stage(ph)
         for name in ("pos", "wp", "t", "rate", "utility_scaled", "done", "conn", "assoc", "obs", "reward", "metrics"):
             ta, tb = getattr(a, name), getattr(b, name)
-            if ta is not None:
+            if ta is None:
+                continue
+            if name in ("obs", "reward", "metrics"):  # summation order of the fused kernel, see above
+                assert torch.allclose(ta, tb, rtol=1e-6, atol=2e-6), (name, k)
+            else:
                 assert torch.equal(ta, tb), (name, k)
     assert _lib.PHASE_ALL == 15
 
@@ -247,7 +251,13 @@ def test_specialised_kernels_equal_generic(scen, mode, handler, E):
         for name in ("pos", "wp", "t", "episode", "rate", "utility_scaled", "done", "conn", "assoc", "obs",
                      "reward", "metrics", "bs_xy", "nbs"):
             ta, tb = getattr(a, name), getattr(b, name)
-            if ta is not None:
+            if ta is None:
+                continue
+            if name in ("obs", "reward", "metrics"):
+                # per-env float sums: the several-UEs-per-thread kernels add in a different (fixed)
+                # order than the shuffle tree, so the last ulp may differ
+                assert torch.allclose(ta, tb, rtol=1e-6, atol=2e-6), (name, k)
+            else:
                 assert torch.equal(ta, tb), (name, k)
 
 
@@ -284,7 +294,7 @@ print(" ".join(out))
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     digests = []
     for flag in ("0", "1"):
-        env = dict(os.environ, MBE_PIPE=flag)
+        env = dict(os.environ, MBE_PIPE=flag, MBE_UPT="0")
         res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
         assert res.returncode == 0, res.stderr[-2000:]
         digests.append(res.stdout.strip().splitlines()[-1])
