@@ -92,6 +92,7 @@ struct UptEntry {
 #ifndef MBE_UPT_K_MEDIUM
 #define MBE_UPT_K_MEDIUM 5
 #endif
+// (small 5x3 with K=1 and large 30x13 with K=10 were measured slower than one thread per UE)
 const UptEntry kUpts[] = {MBE_UPT(0, 15, 4, MBE_UPT_K_MEDIUM), MBE_UPT(1, 15, 4, MBE_UPT_K_MEDIUM)};
 
 const SpecEntry kSpecs[] = {
