@@ -16,6 +16,7 @@
 #include "mbe_step_spec.cuh"
 #include "mbe_step_big.cuh"
 #include "mbe_step_upt.cuh"
+#include "mbe_step_tpe.cuh"
 
 namespace {
 
@@ -60,6 +61,10 @@ struct mbe_env {
   void (*upt)(mbe::StepArgs) = nullptr;
   size_t upt_smem = 0;
   int upt_epb = 0;
+  // thread-per-env FORK kernel (per-env layouts, E % 32 == 0, 16-byte aligned buffers)
+  void (*tpe)(mbe::StepArgs) = nullptr;
+  size_t tpe_smem = 0;
+  bool tpe_bound_ok = false;
 };
 
 namespace {
@@ -294,6 +299,15 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
           env->upt_epb = (32 / t.K) * MBE_UPT_WARPS;
         }
   }
+  {
+    const char* v = std::getenv("MBE_TPE");
+    const bool on = !(v && v[0] == '0');
+    if (on && !gym && a.bs_per_env && cfg->num_classes == 1 && !env->big && a.E % 32 == 0 && a.U == 7 && a.B == 10 &&
+        !(cfg->flags & MBE_FLAG_GENERIC_KERNEL)) {
+      env->tpe = mbe::step_tpe_fork_kernel<7, 10>;
+      env->tpe_smem = sizeof(mbe::TpeForkSmem<7, 10>);
+    }
+  }
   env->smem = env->big ? 0 : mbe::smem_bytes(gym, ma, a.epb, a.U, a.B, a.F, a.bs_per_env);
   env->grid = env->big ? a.E : (a.E + a.epb - 1) / a.epb;
   if (env->big) env->spec = nullptr;
@@ -314,6 +328,8 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
                              (int)env->spec_smem);
   if (e == cudaSuccess && env->upt)
     e = cudaFuncSetAttribute((const void*)env->upt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->upt_smem);
+  if (e == cudaSuccess && env->tpe)
+    e = cudaFuncSetAttribute((const void*)env->tpe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->tpe_smem);
   if (e == cudaSuccess && env->pipe) {
     // measured slower than the one-chunk-per-CTA kernel on B200 (profiles/README.md): opt-in only
     const char* v = std::getenv("MBE_PIPE");
@@ -381,6 +397,13 @@ int mbe_bind(mbe_env* env, const mbe_buffers* b) {
   a.wp_cnt = b->wp_cnt;
   a.inj_k = b->inj_k;
   a.obs_bulk_ok = b->obs && (((uintptr_t)b->obs & 15) == 0);
+  {
+    uintptr_t all = (uintptr_t)b->pos | (uintptr_t)b->wp | (uintptr_t)b->t | (uintptr_t)b->episode |
+                    (uintptr_t)b->bs_xy | (uintptr_t)b->nbs | (uintptr_t)b->assoc | (uintptr_t)b->rate |
+                    (uintptr_t)b->utility | (uintptr_t)b->done | (uintptr_t)b->metrics;
+    // bulk async copies need 16-byte aligned global addresses; the FORK thread-per-env kernel also needs nbs
+    env->tpe_bound_ok = (all & 15) == 0 && b->nbs != nullptr;
+  }
   if (!a.bs_per_env) {
     // a shared layout is constant for the life of the binding: fold the coordinates into the
     // kernel parameters (constant bank) for the specialised kernels
@@ -417,6 +440,21 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
     else
       mbe::step_big_kernel<1, 1><<<env->grid, mbe::kBigThreads, sizeof(mbe::BigSmem), st>>>(a);
     MBE_CUDA(cudaGetLastError());
+    env->launches += 1;
+    return 0;
+  }
+  if (env->tpe && env->tpe_bound_ok && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr && !a.inj_wp) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(a.E / 32);
+    lc.blockDim = dim3(32);
+    lc.dynamicSmemBytes = env->tpe_smem;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    MBE_CUDA(cudaLaunchKernelEx(&lc, env->tpe, a));
     env->launches += 1;
     return 0;
   }

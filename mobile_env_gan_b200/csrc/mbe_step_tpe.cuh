@@ -1,0 +1,199 @@
+// "Thread per env" fused FORK step (the reference's real step, base.py:230-296) for per-env BS
+// layouts (MComCustom: 7 UEs, up to 10 random BSs per env): a CTA is ONE warp and owns 32
+// consecutive envs; lane e walks the U UEs and B BS slots of its env in scalar code -- no ballots,
+// no match, no shuffles, no idle lanes, and the per-env work (clock, metrics, BS table) is paid
+// once per env instead of once per UE.  The FORK step has no observation, so an env needs only
+// ~200 bytes of shared memory and occupancy is not limited by it (the same mapping for the GYM
+// step was occupancy-bound by its 1 KB/env observation staging, profiles/README.md).
+// Every global stream of the 32 envs is one contiguous slice: all HBM traffic is bulk async
+// copies (TMA) -- 6 loads tracked by an mbarrier, 8-11 stores.
+// Sums replay the association order of the warp-segment kernels' shuffle tree, so all outputs are
+// bit-identical to them.
+// Preconditions (dispatcher): FORK mode, per-env layout, one BS class, E % 32 == 0, exact-FP32
+// squared distances not needed (integer only), no debug / injection buffers, all stream bases
+// 16-byte aligned, nbs bound.
+#pragma once
+#include "mbe_device.cuh"
+#include "mbe_step_spec.cuh"  // mbar_* / bulk_load helpers
+
+namespace mbe {
+
+template <int U, int B>
+struct TpeForkSmem {
+  alignas(16) uint32_t pos[32 * U];
+  alignas(16) uint32_t wp[32 * U];
+  alignas(16) uint32_t bs[32 * B];
+  alignas(16) int32_t nbs[32];
+  alignas(16) int32_t t[32];
+  alignas(16) int32_t epi[32];
+  alignas(16) int32_t assoc[32 * U];
+  alignas(16) double rate[32 * U];
+  alignas(16) float util[32 * U];
+  alignas(16) float metrics[32 * 4];
+  alignas(16) uint8_t done[32];
+  alignas(8) uint64_t bar;
+};
+
+// the shuffle tree of seg_sum / seg_sum_head (mbe_device.cuh) replayed on a thread-local array:
+// v[u] += v[u+off] for off = 1, 2, 4, ... where every lane reads pre-step values
+template <int U>
+__device__ __forceinline__ float tree_sum(float (&v)[U]) {
+#pragma unroll
+  for (int off = 1; off < U; off <<= 1) {
+#pragma unroll
+    for (int u = 0; u + off < U; ++u) v[u] += v[u + off];  // ascending u: v[u+off] is still the old value
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+
+template <int U, int B>
+__global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using S = TpeForkSmem<U, B>;
+  static_assert(B <= 16, "per-BS counts are packed 4 bits per BS into 64 bits");
+  S& s = *reinterpret_cast<S*>(smem_raw);
+  const int lane = threadIdx.x;
+  const size_t e0 = (size_t)blockIdx.x * 32;  // first env of this warp
+  const int env = (int)e0 + lane;
+  const unsigned gid = a.env_offset + (unsigned)env;
+  const SlotDev& C0 = a.slot[0];  // the single BS class
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // ---- state slices of the 32 envs -> shared memory (bulk async copies) ----
+  constexpr uint32_t EU = 32 * U * 4, EB = 32 * B * 4, EE = 32 * 4;
+  if (lane == 0) {
+    mbar_init(&s.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&s.bar, 2 * EU + EB + 3 * EE);
+    bulk_load(s.pos, a.pos + e0 * U, EU, &s.bar);
+    bulk_load(s.wp, a.wp + e0 * U, EU, &s.bar);
+    bulk_load(s.bs, a.bs_xy + e0 * B, EB, &s.bar);
+    bulk_load(s.nbs, a.nbs + e0, EE, &s.bar);
+    bulk_load(s.t, a.t + e0, EE, &s.bar);
+    bulk_load(s.epi, a.episode + e0, EE, &s.bar);
+  }
+  __syncwarp();
+  mbar_wait(&s.bar, 0);
+
+  uint32_t* my_pos = s.pos + lane * U;
+  uint32_t* my_wp = s.wp + lane * U;
+  uint32_t* my_bs = s.bs + lane * B;
+  int t_e = s.t[lane], epi = s.epi[lane], nb = s.nbs[lane];
+
+  int bx[B], by[B];
+#pragma unroll
+  for (int b = 0; b < B; ++b) unpack_xy(my_bs[b], bx[b], by[b]);
+
+  // ---- move (movement.py:42-62), then nearest connectable BS (base.py:236-241) ----
+  int best[U], bestd2[U];
+  unsigned long long packed = 0ull;  // |connections(b)|, 4 bits per BS
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    int x, y, wx, wy;
+    unpack_xy(my_pos[u], x, y);
+    unpack_xy(my_wp[u], wx, wy);
+    if (wx < 0)
+      philox_point(a, gid, (unsigned)u, (unsigned)t_e, P_WAYPOINT, a.reset_rng_episode ? 0u : (unsigned)epi, wx, wy);
+    if (move_ue(a, x, y, wx, wy)) wx = wy = -1;
+    my_pos[u] = pack_xy(x, y);
+    my_wp[u] = pack_xy(wx, wy);
+    int bb = -1, bd = 0x7fffffff;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      const int dx = x - bx[b], dy = y - by[b];
+      const int d2 = dx * dx + dy * dy;
+      if (b < nb && d2 <= C0.d2max && d2 < bd) {  // strict <: first minimum wins (base.py:240)
+        bb = b;
+        bd = d2;
+      }
+    }
+    best[u] = bb;
+    bestd2[u] = bd;
+    if (bb >= 0) packed += 1ull << (4 * bb);
+  }
+
+  // ---- ResourceFair split + rounding (schedules.py:20-22, base.py:435), utility (253-258) ----
+  const double* lut = C0.lutn;
+  const unsigned stride = (unsigned)C0.stride;
+  float uv[U], rv[U];
+  int nconn = 0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    double rate = 0.0;
+    if (best[u] >= 0) {
+      const unsigned n = (unsigned)(packed >> (4 * best[u])) & 15u;
+      rate = lut[n * stride + (unsigned)bestd2[u]];
+      nconn += 1;
+    }
+    const float util = scaled_utility(a, rate);
+    s.assoc[lane * U + u] = best[u];
+    s.rate[lane * U + u] = rate;
+    s.util[lane * U + u] = util;
+    uv[u] = util;
+    rv[u] = (float)rate;
+  }
+  {
+    const float usum = tree_sum<U>(uv), rsum = tree_sum<U>(rv);
+    const float nc = (float)nconn;
+    reinterpret_cast<float4*>(s.metrics)[lane] = make_float4(nc, nc, usum * a.inv_U, mean_or_zero(rsum, nc));
+  }
+
+  // ---- clock, same-step autoreset (base.py:280-291, 407-409; 172-209; custom.py:40-77) ----
+  t_e += 1;
+  const bool done = t_e >= a.ep_time;
+  s.done[lane] = done ? 1 : 0;
+  if (done && a.autoreset) {
+    epi += 1;
+    t_e = 0;
+#pragma unroll 1
+    for (int u = 0; u < U; ++u) {
+      int x, y;
+      philox_point(a, gid, (unsigned)u, 0u, P_INITPOS, a.reset_rng_episode ? 0u : (unsigned)epi, x, y);
+      my_pos[u] = pack_xy(x, y);
+      my_wp[u] = pack_xy(-1, -1);
+    }
+    if (a.bs_rand_max > 0) {  // generate_base_stations (custom.py:68-77)
+      nb = philox_bs_count(a, gid, (unsigned)epi);
+#pragma unroll 1
+      for (int b = 0; b < B; ++b) {
+        int x = 0, y = 0;
+        if (b < nb) philox_point(a, gid, (unsigned)b, 0u, P_BSLAYOUT, (unsigned)epi, x, y);
+        my_bs[b] = pack_xy(x, y);
+      }
+    }
+  }
+  s.t[lane] = t_e;
+  s.epi[lane] = epi;
+  s.nbs[lane] = nb;
+
+  // ---- everything leaves as bulk async stores ----
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    bulk_store(a.pos + e0 * U, s.pos, EU);
+    bulk_store(a.wp + e0 * U, s.wp, EU);
+    bulk_store(a.assoc + e0 * U, s.assoc, EU);
+    if (a.rate) bulk_store(a.rate + e0 * U, s.rate, 2 * EU);
+    bulk_store(a.utility + e0 * U, s.util, EU);
+    if (a.metrics) bulk_store(a.metrics + e0 * 4, s.metrics, 4 * EE);
+    bulk_store(a.done + e0, s.done, 32);
+    bulk_store(a.t + e0, s.t, EE);
+    bulk_store(a.episode + e0, s.epi, EE);
+    if (a.bs_rand_max > 0) {
+      bulk_store(a.bs_xy + e0 * B, s.bs, EB);
+      bulk_store(a.nbs + e0, s.nbs, EE);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+
+}  // namespace mbe

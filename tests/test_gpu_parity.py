@@ -94,12 +94,12 @@ def test_fork_replays_reference_trajectory(name):
 
 
 # --------------------------------------------------------------------- FORK, Philox driven
+@pytest.mark.parametrize("E", [777, 800])  # 777: warp-segment kernel (ragged tail); 800: thread-per-env kernel
 @pytest.mark.parametrize("autoreset", [False, True])
-def test_fork_random_layouts_match_oracle(autoreset):
+def test_fork_random_layouts_match_oracle(autoreset, E):
     """MComCustom-style: random BS layout per env and episode, Philox waypoints."""
     from mobile_env_gan_b200.scenarios import MComCustom
 
-    E = 777  # not a multiple of the envs per block
     env = MComCustom(config={"num_envs": E, "autoreset": autoreset, "env_offset": 12345,
                              "movement_params": {"reset_rng_episode": False}})
     mir = Mirror(env)
