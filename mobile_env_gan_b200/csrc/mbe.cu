@@ -176,6 +176,9 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   a.width = cfg->width;
   a.height = cfg->height;
   a.velocity = cfg->velocity;
+  a.wh_int = (cfg->width == std::floor(cfg->width) && cfg->height == std::floor(cfg->height)) ? 1 : 0;
+  a.wh_int_w = (int)cfg->width;
+  a.wh_int_h = (int)cfg->height;
   a.velocity_f = (float)cfg->velocity;
   a.tie_eps = (float)(cfg->velocity * 1e-6 + 1e-6);
   {  // is an axis-aligned step exactly +-velocity in the reference's FP64 chain (movement.py:58-59)?
@@ -303,6 +306,7 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     const char* v = std::getenv("MBE_TPE");
     const bool on = !(v && v[0] == '0');
     if (on && !gym && a.bs_per_env && cfg->num_classes == 1 && !env->big && a.E % 32 == 0 && a.U == 7 && a.B == 10 &&
+        cfg->width <= 2048 && cfg->height <= 2048 &&
         !(cfg->flags & MBE_FLAG_GENERIC_KERNEL)) {
       env->tpe = mbe::step_tpe_fork_kernel<7, 10>;
       env->tpe_smem = sizeof(mbe::TpeForkSmem<7, 10>);

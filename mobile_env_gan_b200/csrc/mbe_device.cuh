@@ -54,6 +54,7 @@ struct StepArgs {
   double width, height, velocity;
   float velocity_f, tie_eps;  // FP32 fast path of the movement and its fallback band
   int axis_exact;             // (velocity*d)/|d| == +-velocity in FP64 for every |d| on the map
+  int wh_int, wh_int_w, wh_int_h;  // width and height are integers (the usual case): integer draws
   int move_d2max;
   // utility: u = clip(util_c * log2(w2 + r), lo, hi); scaled = (u - lo) * util_scale - 1
   float util_c, util_w2, util_lo, util_hi, util_scale;
@@ -109,8 +110,13 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 __device__ __forceinline__ void philox_point(const StepArgs& a, unsigned gid, unsigned ue, unsigned t,
                                           unsigned purpose, unsigned salt, int& x, int& y) {
   uint4 r = philox4x32_10(make_uint4(gid, ue, t, purpose + 4u * salt), make_uint2(a.seed_lo, a.seed_hi));
-  x = (int)((double)r.x * 0x1p-32 * a.width);
-  y = (int)((double)r.y * 0x1p-32 * a.height);
+  if (a.wh_int) {  // integer map size: floor(r * 2^-32 * W) is exactly the high word of r * W
+    x = (int)__umulhi(r.x, (unsigned)a.wh_int_w);
+    y = (int)__umulhi(r.y, (unsigned)a.wh_int_h);
+  } else {
+    x = (int)((double)r.x * 0x1p-32 * a.width);
+    y = (int)((double)r.y * 0x1p-32 * a.height);
+  }
 }
 
 __device__ __forceinline__ int philox_bs_count(const StepArgs& a, unsigned gid, unsigned salt) {

@@ -10,8 +10,8 @@
 // Sums replay the association order of the warp-segment kernels' shuffle tree, so all outputs are
 // bit-identical to them.
 // Preconditions (dispatcher): FORK mode, per-env layout, one BS class, E % 32 == 0, exact-FP32
-// squared distances not needed (integer only), no debug / injection buffers, all stream bases
-// 16-byte aligned, nbs bound.
+// map no larger than 2048 x 2048 (the packed nearest-BS key must not overflow), no debug / injection buffers, all
+// stream bases 16-byte aligned, nbs bound.
 #pragma once
 #include "mbe_device.cuh"
 #include "mbe_step_spec.cuh"  // mbar_* / bulk_load helpers
@@ -88,9 +88,13 @@ __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant
   uint32_t* my_bs = s.bs + lane * B;
   int t_e = s.t[lane], epi = s.epi[lane], nb = s.nbs[lane];
 
+  // absent slots (b >= nb) are parked far outside the map: they can never be the nearest BS
   int bx[B], by[B];
 #pragma unroll
-  for (int b = 0; b < B; ++b) unpack_xy(my_bs[b], bx[b], by[b]);
+  for (int b = 0; b < B; ++b) {
+    unpack_xy(my_bs[b], bx[b], by[b]);
+    if (b >= nb) bx[b] = by[b] = -6000;  // 2*(6000+2048)^2 << 4 still fits int32; > any d2max on such a map
+  }
 
   // ---- move (movement.py:42-62), then nearest connectable BS (base.py:236-241) ----
   int best[U], bestd2[U];
@@ -105,16 +109,16 @@ __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant
     if (move_ue(a, x, y, wx, wy)) wx = wy = -1;
     my_pos[u] = pack_xy(x, y);
     my_wp[u] = pack_xy(wx, wy);
-    int bb = -1, bd = 0x7fffffff;
+    // nearest BS = min over (d2 << 4 | b): lowest b wins a distance tie like Python's min
+    // (base.py:240); with a single BS class it is connectable iff its d2 <= d2max (base.py:212-214)
+    int key = 0x7fffffff;
 #pragma unroll
     for (int b = 0; b < B; ++b) {
       const int dx = x - bx[b], dy = y - by[b];
-      const int d2 = dx * dx + dy * dy;
-      if (b < nb && d2 <= C0.d2max && d2 < bd) {  // strict <: first minimum wins (base.py:240)
-        bb = b;
-        bd = d2;
-      }
+      key = min(key, ((dx * dx + dy * dy) << 4) | b);
     }
+    const int bd = key >> 4;
+    const int bb = (bd <= C0.d2max) ? (key & 15) : -1;
     best[u] = bb;
     bestd2[u] = bd;
     if (bb >= 0) packed += 1ull << (4 * bb);
