@@ -324,11 +324,23 @@ def main():
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         checksum = float(host["utility_scaled"].sum()) if fork else float(rew_h.sum())
+        # secondary figure: the deployment the step is built for -- the observation stays in the policy's
+        # input tensor on the device, only reward and done come back to the host
+        e2e_lite = None
+        if not fork:
+            for i in range(3):
+                envs[i % R].step_host(acts_h[i % 2], None, rew_h, done_h)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                envs[i % R].step_host(acts_h[i % 2], None, rew_h, done_h)
+            torch.cuda.synchronize()
+            e2e_lite = (time.perf_counter() - t0, rew_h.numel() * 4 + E)
 
-    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms, e2e_s * 1e3, (e2e_lite[0] if e2e_lite else 0.0) * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(times[0]), float(times[1])
+    ms, e2e_ms, lite_ms = float(times[0]), float(times[1]), float(times[2])
     if rank == 0:
         peak, peak_src = measured_peak()
         per_launch_s = ms * 1e-3 / args.steps
@@ -355,7 +367,11 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": world * E * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": api, "cpu_affinity": affinity,
-                    "checksum": checksum},
+                    "checksum": checksum,
+                    "obs_stays_on_device": None if not e2e_lite else {
+                        "value": world * E * e2e_steps / (lite_ms * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": e2e_lite[1],
+                        "note": "same call with obs_host=NULL: actions in, reward+done out"}},
             "gpu_launches": gpu_launches,
             "clocks": sampler.result(),
         }
