@@ -69,6 +69,14 @@ struct mbe_env {
 
 namespace {
 
+bool pdl_enabled() {
+  static const bool on = []() {
+    const char* v = std::getenv("MBE_PDL");
+    return v && v[0] == '1';
+  }();
+  return on;
+}
+
 struct SpecEntry {
   int mode, handler, U, B, per_env;
   void (*fn)(mbe::StepArgs);
@@ -457,7 +465,7 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
-    lc.numAttrs = 1;
+    lc.numAttrs = pdl_enabled() ? 1 : 0;
     MBE_CUDA(cudaLaunchKernelEx(&lc, env->tpe, a));
     env->launches += 1;
     return 0;
@@ -473,7 +481,7 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
-    lc.numAttrs = 1;
+    lc.numAttrs = pdl_enabled() ? 1 : 0;
     MBE_CUDA(cudaLaunchKernelEx(&lc, env->upt, a));
     env->launches += 1;
     return 0;
@@ -482,8 +490,10 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
   if (env->spec && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr && !a.inj_wp)
   {
     static const bool pdl = []() {
+      // programmatic dependent launch: neutral for the current medium / custom kernels, harmful for
+      // 8 us kernels (early-resident dependents steal CTA slots) -- opt-in (profiles/README.md)
       const char* v = std::getenv("MBE_PDL");
-      return !(v && v[0] == '0');
+      return v && v[0] == '1';
     }();
     cudaLaunchConfig_t lc = {};
     const bool use_pipe = env->pipe != nullptr;
