@@ -25,14 +25,14 @@ import torch
 
 from .. import _lib
 from . import metrics as _metrics
-from .arrival import Arrival, NoDeparture
+from .arrival import NoDeparture
 from .channels import Channel, OkumuraHata
 from .entities import BaseStation, UserEquipment
 from .logging import Monitor
-from .movement import Movement, RandomWaypointMovement
-from .schedules import ProportionalFair, ResourceFair, Scheduler
+from .movement import RandomWaypointMovement
+from .schedules import ProportionalFair, ResourceFair
 from .util import deep_dict_merge
-from .utilities import BoundedLogUtility, Utility
+from .utilities import BoundedLogUtility
 
 MAX_COORD = 32767
 

@@ -489,12 +489,7 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
   // debug SNR output and waypoint injection only exist in the generic kernel
   if (env->spec && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr && !a.inj_wp)
   {
-    static const bool pdl = []() {
-      // programmatic dependent launch: neutral for the current medium / custom kernels, harmful for
-      // 8 us kernels (early-resident dependents steal CTA slots) -- opt-in (profiles/README.md)
-      const char* v = std::getenv("MBE_PDL");
-      return v && v[0] == '1';
-    }();
+    const bool pdl = pdl_enabled();
     cudaLaunchConfig_t lc = {};
     const bool use_pipe = env->pipe != nullptr;
     lc.gridDim = dim3(use_pipe ? env->pipe_grid : env->grid);
