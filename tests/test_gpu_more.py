@@ -168,6 +168,43 @@ def test_ma_million_env_slice_is_offset_invariant():
         assert torch.equal(oa, ob[1000:]) and torch.equal(ra, rb[1000:])
 
 
+@pytest.mark.parametrize("wid,E", [("mobile-medium-central-v0", 96), ("mobile-medium-ma-v0", 96),
+                                   ("mobile-large-central-v0", 64), ("mobile-small-ma-v0", 96),
+                                   ("mobile-custom-v0", 96), ("mobile-custom-v0", 70)])
+def test_soak_many_episodes_against_oracle(wid, E):
+    """400 steps (20 episodes with same-step autoreset) of every default kernel family against the
+    oracle: rare paths (waypoint redraws, FP64 tie fallback, re-initialisation, layout regeneration)
+    are all exercised many times."""
+    import mobile_env_gan_b200 as mbe
+
+    env = mbe.make(wid, num_envs=E, autoreset=True, env_offset=777,
+                   config={"movement_params": {"reset_rng_episode": False}})
+    mir = Mirror(env)
+    env.reset(), mir.reset()
+    gym = env.actions is not None
+    rng = np.random.default_rng(9)
+    B, U = env.plan.num_bs, env.plan.num_ues
+    for k in range(400):
+        if gym:
+            acts = rng.integers(0, B + 1, size=(E, U)).astype(np.int32)
+            obs, rew, _, trunc, _ = env.step(torch.from_numpy(acts).cuda())
+            out = mir.step_gym(acts)
+            if k % 7 == 0 or out["done"].any():
+                assert np.array_equal(env.conn.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, conn_bits(out["conn_after"])), k
+                assert np.array_equal(env.rate.cpu().numpy(), out["rate"]), k
+                close(obs.cpu().numpy().reshape(E, U, -1), out["obs"], f"obs {k}")
+                close(rew.cpu(), out["reward"], f"reward {k}")
+        else:
+            env.step(0, k)
+            out = mir.step_fork()
+            if k % 7 == 0 or out["done"].any():
+                assert np.array_equal(env.assoc.cpu().numpy(), out["assoc"]), k
+                assert np.array_equal(env.rate.cpu().numpy(), out["rate"]), k
+                assert np.array_equal(env.bs_xy.cpu().numpy(), mir.bs), k
+        assert np.array_equal(env.pos.cpu().numpy(), out["pos_after"]), k
+    assert int(env.episode.max()) == 20
+
+
 def _nccl_worker(rank, world, port, q):
     import torch.distributed as dist
 
