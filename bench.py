@@ -125,12 +125,15 @@ def run_reference(args, rank, world):
     workload = args.workload
     procs = os.cpu_count() or 1
     total_steps = args.warmup + args.steps
-    seconds = max(0.5, min(5.0, 60.0 / max(total_steps, 1)))
+    # every step is a bounded sample; the whole run is held to about two minutes whatever K is
+    seconds = max(0.02, min(5.0, 120.0 / max(total_steps, 1)))
+    runner = cpu_baseline.Runner(workload, procs)
     vals = []
     for i in range(total_steps):
-        r = cpu_baseline.run(workload, seconds, procs)
+        r = runner.step(seconds)
         if i >= args.warmup:
             vals.append(r)
+    runner.close()
     value = statistics.mean(v["value"] for v in vals)
     B, U = SIZES[workload.rsplit("-", 2)[0]]
     line = {

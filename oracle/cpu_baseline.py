@@ -57,13 +57,7 @@ def _worker(args):
     return steps, time.perf_counter() - t0
 
 
-def run(workload: str, seconds: float = 5.0, procs: int | None = None):
-    """Steps independent envs of ``workload`` on ``procs`` host processes for ``seconds`` each.
-    Returns dict(value=env-steps/s aggregate, cores, single_core, sample)."""
-    procs = procs or os.cpu_count() or 1
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_worker, [(workload, seconds, 1000 + i) for i in range(procs)])
+def _summary(workload, procs, seconds, res):
     total = sum(s for s, _ in res)
     wall = max(t for _, t in res)
     return {
@@ -72,6 +66,36 @@ def run(workload: str, seconds: float = 5.0, procs: int | None = None):
         "cores": procs,
         "kind": "port",
         "single_core": float(np.mean([s / t for s, t in res])),
-        "sample": f"{procs} procs x {seconds:.0f} s of {workload} (scalar port of MComCore.step, "
+        "sample": f"{procs} procs x {seconds:.2f} s of {workload} (scalar port of MComCore.step, "
                   f"one env per process, {total} env-steps)",
     }
+
+
+def run(workload: str, seconds: float = 5.0, procs: int | None = None):
+    """Steps independent envs of ``workload`` on ``procs`` host processes for ``seconds`` each.
+    Returns dict(value=env-steps/s aggregate, cores, single_core, sample)."""
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_worker, [(workload, seconds, 1000 + i) for i in range(procs)])
+    return _summary(workload, procs, seconds, res)
+
+
+class Runner:
+    """Persistent worker pool for the ``--impl reference`` arm: one call of ``step`` = every host
+    core steps its own env for ``seconds`` (a bounded sample of the workload)."""
+
+    def __init__(self, workload: str, procs: int | None = None):
+        self.workload = workload
+        self.procs = procs or os.cpu_count() or 1
+        self.pool = mp.get_context("spawn").Pool(self.procs)
+        self.calls = 0
+
+    def step(self, seconds: float):
+        self.calls += 1
+        args = [(self.workload, seconds, 1000 * self.calls + i) for i in range(self.procs)]
+        return _summary(self.workload, self.procs, seconds, self.pool.map(_worker, args))
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
