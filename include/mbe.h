@@ -16,7 +16,7 @@
  *   - one handle per device; a handle is not thread-safe, different handles are.
  *
  * Shapes: U <= 32 and B <= 32 run on the warp-segment kernels (one thread per UE, an env is a
- * slice of a warp); 32 < U <= 1024 or 32 < B <= 64, and the ProportionalFair scheduler, run on the
+ * slice of a warp); 32 < U <= 1024 or 32 < B <= 64, and the ProportionalFair / RateFair schedulers, run on the
  * block-per-env kernel (fused mbe_step / mbe_reset only; no mbe_stage / mbe_observe).
  *
  * Data layout (structure of arrays, env-major; E = envs on this rank, U = UEs, B = BS slots,
@@ -52,7 +52,7 @@ extern "C" {
 
 enum { MBE_MODE_FORK = 0, MBE_MODE_GYM = 1 };
 enum { MBE_HANDLER_CENTRAL = 0, MBE_HANDLER_MA = 1 };
-enum { MBE_SCHED_RESOURCE_FAIR = 0, MBE_SCHED_PROPORTIONAL_FAIR = 1 };
+enum { MBE_SCHED_RESOURCE_FAIR = 0, MBE_SCHED_PROPORTIONAL_FAIR = 1, MBE_SCHED_RATE_FAIR = 2 };
 enum { MBE_BS_SHARED = 0, MBE_BS_PER_ENV = 1 };
 enum { MBE_MAX_CLASSES = 8 };
 /* mbe_config.flags */

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("MBE_LIB_PATH") or os.path.join(HERE, "csrc", "libmbe.
 MBE_ABI_VERSION = 1
 MODE_FORK, MODE_GYM = 0, 1
 HANDLER_CENTRAL, HANDLER_MA = 0, 1
-SCHED_RESOURCE_FAIR, SCHED_PROPORTIONAL_FAIR = 0, 1
+SCHED_RESOURCE_FAIR, SCHED_PROPORTIONAL_FAIR, SCHED_RATE_FAIR = 0, 1, 2
 BS_SHARED, BS_PER_ENV = 0, 1
 MAX_CLASSES = 8
 FLAG_GENERIC_KERNEL = 1

@@ -30,7 +30,7 @@ from .channels import Channel, OkumuraHata
 from .entities import BaseStation, UserEquipment
 from .logging import Monitor
 from .movement import RandomWaypointMovement
-from .schedules import ProportionalFair, ResourceFair
+from .schedules import ProportionalFair, RateFair, ResourceFair
 from .util import deep_dict_merge
 from .utilities import BoundedLogUtility
 
@@ -128,9 +128,9 @@ class MComCore:
         arrival, channel, scheduler, movement, utility = plugins
         if not isinstance(arrival, NoDeparture):
             raise NotImplementedError(f"arrival {type(arrival).__name__}: only NoDeparture has a CUDA kernel")
-        if not isinstance(scheduler, (ResourceFair, ProportionalFair)):
+        if not isinstance(scheduler, (ResourceFair, ProportionalFair, RateFair)):
             raise NotImplementedError(
-                f"scheduler {type(scheduler).__name__}: only ResourceFair / ProportionalFair have CUDA kernels")
+                f"scheduler {type(scheduler).__name__}: only ResourceFair / ProportionalFair / RateFair have CUDA kernels")
         if not isinstance(utility, BoundedLogUtility):
             raise NotImplementedError(f"utility {type(utility).__name__}: only BoundedLogUtility has a CUDA kernel")
         if not isinstance(channel, Channel):

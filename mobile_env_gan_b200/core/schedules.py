@@ -41,8 +41,13 @@ class ProportionalFair(Scheduler):
 
 
 class RateFair(Scheduler):
-    """Listed for completeness: the reference's RateFair.share returns a scalar
-    (schedules.py:26-29) and cannot be used by allocateDataRate2User (base.py:435)."""
+    """Every UE of a BS receives the same rate ``1 / sum(1 / r_i)``.  The fork computes this scalar
+    but returns it instead of a list (schedules.py:26-29), which allocateDataRate2User (base.py:435)
+    cannot consume; this is the repaired form, with the sum of inverse rates accumulated in 2^-50
+    fixed point (order independent, see oracle/mbe_oracle.py:rate_fair_share).  Parity unpinned."""
+
+    kernel_id = 2
 
     def share(self, bs, rates):
-        raise NotImplementedError("RateFair is broken in the reference (returns a scalar); not built")
+        total = float(sum(int(round(2.0**50 / float(r))) for r in rates)) * 2.0**-50
+        return [1.0 / total for _ in rates]

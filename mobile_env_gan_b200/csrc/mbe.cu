@@ -139,7 +139,8 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   if (cfg->mode != MBE_MODE_FORK && cfg->mode != MBE_MODE_GYM) return fail("mbe_create: bad mode %d", cfg->mode);
   if (cfg->handler != MBE_HANDLER_CENTRAL && cfg->handler != MBE_HANDLER_MA)
     return fail("mbe_create: bad handler %d", cfg->handler);
-  if (cfg->scheduler != MBE_SCHED_RESOURCE_FAIR && cfg->scheduler != MBE_SCHED_PROPORTIONAL_FAIR)
+  if (cfg->scheduler != MBE_SCHED_RESOURCE_FAIR && cfg->scheduler != MBE_SCHED_PROPORTIONAL_FAIR &&
+      cfg->scheduler != MBE_SCHED_RATE_FAIR)
     return fail("mbe_create: scheduler %d not available", cfg->scheduler);
   if (cfg->num_classes < 1 || cfg->num_classes > MBE_MAX_CLASSES)
     return fail("mbe_create: num_classes=%d out of range", cfg->num_classes);
@@ -167,7 +168,7 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   a.U = cfg->num_ues;
   a.B = cfg->num_bs;
   const bool gym = cfg->mode == MBE_MODE_GYM, ma = cfg->handler == MBE_HANDLER_MA;
-  env->big = a.U > 32 || a.B > 32 || cfg->scheduler == MBE_SCHED_PROPORTIONAL_FAIR;
+  env->big = a.U > 32 || a.B > 32 || cfg->scheduler != MBE_SCHED_RESOURCE_FAIR;
   a.scheduler = cfg->scheduler;
   a.F = gym ? (ma ? 4 * a.B + 1 : 2 * a.B + 1) : 0;
   a.epw = env->big ? 1 : 32 / a.U;

@@ -60,7 +60,7 @@ struct StepArgs {
   float util_c, util_w2, util_lo, util_hi, util_scale;
   float inv_U;  // 1/U for the per-env means
   int n_classes;
-  int scheduler;  // 0 ResourceFair, 1 ProportionalFair (block-per-env kernel only)
+  int scheduler;  // 0 ResourceFair; 1 ProportionalFair, 2 RateFair (block-per-env kernel only)
   ClassDev cls[8];
   SlotDev slot[kMaxSlots];
   const uint8_t* bs_class;  // device [B] or nullptr

@@ -48,6 +48,9 @@ __device__ __forceinline__ double link_share(const StepArgs& a, const ClassDev& 
   if (a.scheduler == 1) {
     const double tot = __ll2double_rn((long long)pf_tot) * (1.0 / 1048576.0);
     share = (raw * raw) / tot;
+  } else if (a.scheduler == 2) {  // RateFair: the same 1 / sum(1/r) for every UE of the BS
+    const double tot = __ll2double_rn((long long)pf_tot) * 0x1p-50;
+    share = 1.0 / tot;
   } else {
     share = raw / (double)n;
   }
@@ -260,6 +263,9 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
           if (a.scheduler == 1) {
             const double raw = a.cls[s.cls[b]].lut0[d2_to(i, b)];
             atomicAdd(&s.pf_tot[b], (unsigned long long)__double2ll_rn(raw * 1048576.0));
+          } else if (a.scheduler == 2) {
+            const double raw = a.cls[s.cls[b]].lut0[d2_to(i, b)];
+            atomicAdd(&s.pf_tot[b], (unsigned long long)__double2ll_rn(0x1p50 / raw));
           }
         }
       }

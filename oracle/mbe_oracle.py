@@ -57,7 +57,7 @@ class Params:
     util_lower: float = -20.0
     util_upper: float = 20.0
     util_coeffs: Sequence[float] = (10.0, 0.0, 10.0)
-    scheduler: str = "resource_fair"  # or "proportional_fair" (not in the fork; spec below)
+    scheduler: str = "resource_fair"  # or "proportional_fair" / "rate_fair" (own specs below)
 
 
 # --------------------------------------------------------------------------------------
@@ -109,6 +109,19 @@ def pf_total(rates) -> float:
     reference iterates a Python set) it is accumulated in 2^-20 fixed point:
     ``total = float(sum(int(rint(r * 2^20)))) * 2^-20``."""
     return float(sum(int(np.rint(np.float64(r) * PF_SCALE)) for r in rates)) * (1.0 / PF_SCALE)
+
+
+RF_SCALE = 2.0**50
+
+
+def rate_fair_share(rates) -> float:
+    """RateFair: every UE of the BS receives the same rate 1 / sum(1 / r_i).  The fork's RateFair
+    (core/schedules.py:26-29) computes exactly this scalar but returns it instead of a list, so
+    allocateDataRate2User (base.py:435) cannot use it; this is the repaired form (parity
+    unpinned).  The sum of inverse rates is accumulated in 2^-50 fixed point so that it does not
+    depend on the summation order: total = float(sum(int(rint(2^50 / r)))) * 2^-50."""
+    tot = float(sum(int(np.rint(RF_SCALE / np.float64(r))) for r in rates)) * (1.0 / RF_SCALE)
+    return 1.0 / tot
 
 
 def int_point_dist(ax, ay, bx, by) -> float:
@@ -229,6 +242,8 @@ class ScalarEnv:
             if self.p.scheduler == "proportional_fair":
                 tot = pf_total(max_alloc)
                 rates = [np.float64(r) * np.float64(r) / tot for r in max_alloc]
+            elif self.p.scheduler == "rate_fair" and max_alloc:
+                rates = [np.float64(rate_fair_share(max_alloc))] * len(max_alloc)
             else:
                 rates = [r / len(max_alloc) for r in max_alloc]  # ResourceFair, schedules.py:20-22
             for u, r in zip(ues, rates):
@@ -424,6 +439,11 @@ def batch_allocate(p: Params, snr, conn):
         tot = fixed.sum(axis=1, keepdims=True).astype(np.float64) * (1.0 / PF_SCALE)  # [E,1,B]
         with np.errstate(divide="ignore", invalid="ignore"):
             share = np.where(conn, raw * raw / tot, 0.0)
+    elif p.scheduler == "rate_fair":
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = np.where(conn, np.rint(RF_SCALE / np.where(conn, raw, 1.0)), 0.0).astype(np.int64)
+            tot = inv.sum(axis=1, keepdims=True).astype(np.float64) * (1.0 / RF_SCALE)  # [E,1,B]
+            share = np.where(conn, 1.0 / tot, 0.0)
     else:
         with np.errstate(divide="ignore", invalid="ignore"):
             share = np.where(conn, raw / n, 0.0)

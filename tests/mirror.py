@@ -15,7 +15,7 @@ def params_from_env(env) -> orc.Params:
         velocity=cfg["ue"]["velocity"], snr_tr=cfg["ue"]["snr_tr"], noise=cfg["ue"]["noise"],
         ue_height=cfg["ue"]["height"], util_lower=cfg["utility_params"]["lower"],
         util_upper=cfg["utility_params"]["upper"], util_coeffs=tuple(cfg["utility_params"]["coeffs"]),
-        scheduler="proportional_fair" if p.scheduler == 1 else "resource_fair",
+        scheduler={0: "resource_fair", 1: "proportional_fair", 2: "rate_fair"}[p.scheduler],
     )
 
 

@@ -391,13 +391,15 @@ WIDE = {
     "wide_rf": (40, 70, 200, "rf"),
     "wide_pf": (40, 70, 200, "pf"),
     "medium_pf": (4, 15, 200, "pf"),
+    "medium_ratefair": (4, 15, 200, "ratefair"),
+    "wide_ratefair": (40, 70, 200, "ratefair"),
     "synthetic": (64, 512, 800, "pf"),  # BASELINE.json configs[4]
     "many_ue": (8, 1024, 300, "rf"),
 }
 
 
 def wide_env(name, mode, handler, E, autoreset, extra=None):
-    from mobile_env_gan_b200.core.schedules import ProportionalFair, ResourceFair
+    from mobile_env_gan_b200.core.schedules import ProportionalFair, RateFair, ResourceFair
 
     B, U, size, sched = WIDE[name]
     rng = np.random.default_rng(B * 1000 + U)
@@ -405,7 +407,7 @@ def wide_env(name, mode, handler, E, autoreset, extra=None):
     cfg = {"num_envs": E, "mode": mode, "handler": handler, "autoreset": autoreset, "width": size, "height": size,
            "movement_params": {"width": size, "height": size, "reset_rng_episode": False},
            "EP_MAX_TIME": 7, "arrival_params": {"ep_time": 7}, "ue": {"velocity": 9},
-           "scheduler": ProportionalFair if sched == "pf" else ResourceFair}
+           "scheduler": {"pf": ProportionalFair, "rf": ResourceFair, "ratefair": RateFair}[sched]}
     cfg.update(extra or {})
     return make_env(bs, U, cfg), B, U
 

@@ -16,7 +16,6 @@ from mobile_env_gan_b200.core.base import MComCore
 from mobile_env_gan_b200.core.channels import LogDistance, OkumuraHata
 from mobile_env_gan_b200.core.entities import BaseStation, UserEquipment
 from mobile_env_gan_b200.core.movement import Movement, RandomWaypointMovement
-from mobile_env_gan_b200.core.schedules import RateFair
 from mobile_env_gan_b200.core.util import deep_dict_merge
 from mobile_env_gan_b200.sharding import shard_envs
 
@@ -92,7 +91,13 @@ def test_config_merge_seeding_and_plan():
 
 
 def test_unsupported_plugins_fail_loudly():
-    cfg = MComCore.seeding(deep_dict_merge(MComCore.default_config(), {"scheduler": RateFair}))
+    from mobile_env_gan_b200.core.schedules import Scheduler
+
+    class Lottery(Scheduler):
+        def share(self, bs, rates):
+            return rates
+
+    cfg = MComCore.seeding(deep_dict_merge(MComCore.default_config(), {"scheduler": Lottery}))
     users = [UserEquipment(0, **cfg["ue"])]
     stations = [BaseStation(0, (1, 1), **cfg["bs"])]
     with pytest.raises(NotImplementedError):

@@ -63,7 +63,7 @@ def test_shards_tile_the_env_range(total, world):
 
 @settings(max_examples=15, deadline=None)
 @given(seed=st.integers(0, 10**6), U=st.integers(1, 9), B=st.integers(1, 6), v=st.sampled_from([0.5, 1.5, 3.0, 10.0]),
-       sched=st.sampled_from(["resource_fair", "proportional_fair"]))
+       sched=st.sampled_from(["resource_fair", "proportional_fair", "rate_fair"]))
 def test_scalar_and_batch_oracles_agree_fork(seed, U, B, v, sched):
     rng = np.random.default_rng(seed)
     p = orc.Params(velocity=v, ep_time=6, scheduler=sched, tx=float(rng.choice([30, 40, 46])))
