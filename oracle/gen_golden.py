@@ -64,14 +64,34 @@ CASES = {
     # distance ties: BSs mirrored around the map centre line, first-min tie-break matters
     "tie_layout": ([(100, 60), (100, 140), (60, 100), (140, 100), (100, 60)], 15,
                    ep_cfg(30, {"ue": {"velocity": 4}}), 30),
+    # non-square map, fast UEs: waypoints are drawn per axis (movement.py:45-46)
+    "nonsquare_fast": ([(30, 40), (150, 60), (270, 30), (210, 100)], 9,
+                       ep_cfg(25, {"width": 300, "height": 120, "ue": {"velocity": 25},
+                                   "movement_params": {"width": 300, "height": 120}}), 25),
+    # another carrier and mast height: different folded constants and cut-off distance
+    "low_freq": ([(40, 40), (160, 40), (100, 160)], 8,
+                 ep_cfg(20, {"bs": {"freq": 900, "height": 30, "tx": 33, "bw": 5e6}, "ue": {"velocity": 6, "height": 2.0}}), 20),
+    # a long episode at the default crawl speed (v = 1.5: many exact .5 rounding ties)
+    "long_crawl": ([(60, 60), (140, 60), (60, 140), (140, 140)], 6, ep_cfg(100), 100),
 }
+
+# per-BS radio overrides (BaseStation keyword names): the reference keeps bw/freq/tx/height per BS
+BS_OVERRIDES = {
+    "two_classes": {1: {"tx": 30}, 3: {"tx": 30, "bw": 18e6}},
+}
+CASES["two_classes"] = ([(50, 50), (150, 50), (50, 150), (150, 150), (100, 100)], 12,
+                        ep_cfg(25, {"ue": {"velocity": 8}}), 25)
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     for name, (bs_xy, nue, cfg, steps) in CASES.items():
-        env = rh.make_fixed_layout_env(bs_xy, nue, config=cfg)
+        over = BS_OVERRIDES.get(name)
+        env = rh.make_fixed_layout_env(bs_xy, nue, config=cfg, bs_over=over)
         rec = rh.record_fork_episode(env, steps)
+        if over:  # oracle-side names (Params fields)
+            ren = {"tx": "tx", "bw": "bw", "freq": "freq", "height": "bs_height"}
+            rec["bs_over"] = [{ren[k]: v for k, v in over.get(i, {}).items()} for i in range(len(bs_xy))]
         p = env.default_config()
         from mobile_env.core.util import deep_dict_merge
 

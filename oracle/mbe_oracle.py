@@ -199,6 +199,7 @@ class ScalarEnv:
     bs_xy: list
     num_ues: int
     wp_source: Optional[object] = None
+    bs_over: Optional[list] = None  # per-BS overrides of bw / freq / tx / bs_height (entities.py:6-22)
     pos: list = field(default_factory=list)
     wp: list = field(default_factory=list)
     wp_count: list = field(default_factory=list)
@@ -225,9 +226,17 @@ class ScalarEnv:
                 self.wp[u] = None
             self.pos[u] = new
 
+    def p_of(self, b) -> Params:
+        """Parameters seen by the link to BS b (the reference keeps bw/freq/tx/height per BS)."""
+        if not self.bs_over or not self.bs_over[b]:
+            return self.p
+        import dataclasses
+
+        return dataclasses.replace(self.p, **self.bs_over[b])
+
     def snr(self, b, u):
         bx, by = self.bs_xy[b]
-        return snr_of(self.p, int_point_dist(bx, by, *self.pos[u]))
+        return snr_of(self.p_of(b), int_point_dist(bx, by, *self.pos[u]))
 
     def connectable(self, b, u):  # base.py:212-214
         return self.snr(b, u) > self.p.snr_tr
@@ -238,7 +247,7 @@ class ScalarEnv:
         pair = {}
         for b, ues in enumerate(bs_conns):
             snrs = [self.snr(b, u) for u in ues]
-            max_alloc = [datarate_of(self.p, s) for s in snrs]
+            max_alloc = [datarate_of(self.p_of(b), s) for s in snrs]
             if self.p.scheduler == "proportional_fair":
                 tot = pf_total(max_alloc)
                 rates = [np.float64(r) * np.float64(r) / tot for r in max_alloc]

@@ -95,7 +95,7 @@ def import_reference():
     return base, entities, custom
 
 
-def make_fixed_layout_env(bs_xy, num_ues, config=None, bs_params=None, ue_params=None):
+def make_fixed_layout_env(bs_xy, num_ues, config=None, bs_params=None, ue_params=None, bs_over=None):
     """Reference env with a fixed BS list (what MComCustom does at custom.py:40-62,
     minus the unseeded ``random`` BS generator) and JSON dumps disabled."""
     base, entities, _ = import_reference()
@@ -122,7 +122,12 @@ def make_fixed_layout_env(bs_xy, num_ues, config=None, bs_params=None, ue_params
     uep = dict(cfg["ue"])
     if ue_params:
         uep.update(ue_params)
-    stations = [entities.BaseStation(i, tuple(xy), **bsp) for i, xy in enumerate(bs_xy)]
+    stations = []
+    for i, xy in enumerate(bs_xy):
+        kw = dict(bsp)
+        if bs_over and bs_over.get(i):
+            kw.update(bs_over[i])  # keys of BaseStation.__init__: bw, freq, tx, height
+        stations.append(entities.BaseStation(i, tuple(xy), **kw))
     users = [entities.UserEquipment(i, **uep) for i in range(num_ues)]
     return FixedLayoutEnv(stations, users, config or {})
 

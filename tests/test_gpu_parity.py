@@ -63,7 +63,22 @@ def test_fork_replays_reference_trajectory(name):
     rec = load_golden(name)
     E = 5  # replicas of the same episode: also checks envs are independent of their slot
     U = len(rec["init_pos"])
-    env = make_env(rec["bs_xy"], U, golden_config(rec, {"num_envs": E, "mode": "fork"}))
+    if rec.get("bs_over"):  # per-BS radio parameters, as the reference's BaseStation objects carry them
+        MComCore, BaseStation, UserEquipment = _mods()
+        from mobile_env_gan_b200.core.util import deep_dict_merge
+
+        config = golden_config(rec, {"num_envs": E, "mode": "fork"})
+        cfg = deep_dict_merge(MComCore.default_config(), config)
+        ren = {"tx": "tx", "bw": "bw", "freq": "freq", "bs_height": "height"}
+        stations = []
+        for i, xy in enumerate(rec["bs_xy"]):
+            kw = dict(cfg["bs"])
+            kw.update({ren[k]: v for k, v in rec["bs_over"][i].items()})
+            stations.append(BaseStation(i, tuple(xy), **kw))
+        env = MComCore(stations, [UserEquipment(i, **cfg["ue"]) for i in range(U)], config)
+        assert len(env.plan.classes) > 1
+    else:
+        env = make_env(rec["bs_xy"], U, golden_config(rec, {"num_envs": E, "mode": "fork"}))
     snr_dbg = env.enable_debug_snr()
     seq = golden_waypoints(rec)
     K = max(1, max(len(s) for s in seq))
