@@ -168,6 +168,60 @@ def dump_golden(name="kat1", steps=20):
     print("dumps", name, n, "files")
 
 
+def custom_epochs_golden(epochs=4, steps=20, seed=123):
+    """The fork's own scenario exactly as shipped (MComCustom, custom.py:12-85): per epoch a fresh
+    BS layout from the global ``random`` (seeded here), the same UE trajectory every epoch
+    (movement reset_rng_episode=True, base.py:130-134), dumps disabled."""
+    import random
+
+    base, entities, custom = rh.import_reference()
+
+    class Quiet(custom.MComCustom):
+        def save_layout_and_data_rates(self, epoch_number, curr_step):
+            return
+
+    random.seed(seed)
+    env = Quiet()
+    out = {"epochs": []}
+    mv = env.movementModel
+    for ep in range(epochs):
+        env.reset()
+        ues = [env.userDict[k] for k in sorted(env.userDict)]
+        bss = [env.stationDict[k] for k in sorted(env.stationDict)]
+        rec = {"bs_xy": [[bs.x, bs.y] for bs in bss], "init_pos": [[int(u.x), int(u.y)] for u in ues], "steps": []}
+        orig = mv.move
+        targets = {}
+
+        def logged(ue, orig=orig):
+            had = ue in mv.userMoveDirection
+            res = orig(ue)
+            wp = mv.userMoveDirection.get(ue, res)
+            targets[ue.ue_id] = (int(wp[0]), int(wp[1]), 0 if had else 1)
+            return res
+
+        mv.move = logged
+        for s in range(steps):
+            targets.clear()
+            env.step(ep, s)
+            conn = [-1] * len(ues)
+            for (bs, ue) in env.bs2ue_dataRates:
+                conn[ue.ue_id] = bs.bs_id
+            rec["steps"].append({
+                "pos": [[int(u.x), int(u.y)] for u in ues],
+                "wp": [list(targets[u.ue_id]) for u in ues],
+                "conn": conn,
+                "rate": [float(env.allUserDataRates.get(u, 0.0)) for u in ues],
+                "utility": [float(env.ue_utilities[u]) for u in ues],
+                "done": bool(env.time_is_up),
+            })
+        mv.move = orig
+        out["epochs"].append(rec)
+    with open(os.path.join(OUT, "custom_epochs.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print("custom_epochs", epochs, "epochs", [len(e["bs_xy"]) for e in out["epochs"]], "BSs")
+
+
 if __name__ == "__main__":
     main()
     dump_golden("kat1")
+    custom_epochs_golden()

@@ -108,6 +108,46 @@ def test_fork_replays_reference_trajectory(name):
             assert np.all(np.isinf(got[~fin]))
 
 
+def test_custom_scenario_epochs_replay_reference():
+    """The fork's scenario as shipped (MComCustom): env e of the batch replays epoch e of the
+    reference -- its own BS layout (5..10 live slots of 10), the shared UE trajectory."""
+    import json
+    import os
+
+    from conftest import GOLDEN_DIR
+    from mobile_env_gan_b200.scenarios import MComCustom
+
+    with open(os.path.join(GOLDEN_DIR, "custom_epochs.json")) as f:
+        epochs = json.load(f)["epochs"]
+    E, U, B = len(epochs), 7, 10
+    for generic in (False, True):
+        env = MComCustom(config={"num_envs": E, "generic_kernel": generic})
+        env.reset()
+        bs = np.zeros((E, B, 2), dtype=np.int16)
+        nbs = np.zeros(E, dtype=np.int32)
+        seqs = [golden_waypoints(ep) for ep in epochs]
+        K = max(len(s) for seq in seqs for s in seq)
+        wp = np.zeros((E, U, K, 2), dtype=np.int16)
+        for e, ep in enumerate(epochs):
+            nbs[e] = len(ep["bs_xy"])
+            bs[e, : nbs[e]] = ep["bs_xy"]
+            for u, s in enumerate(seqs[e]):
+                for k, w in enumerate(s):
+                    wp[e, u, k] = w
+        env.set_station_positions(bs, nbs)
+        env.inject_waypoints(wp)
+        env.set_positions(np.array([ep["init_pos"] for ep in epochs]))
+        for k in range(len(epochs[0]["steps"])):
+            env.step(0, k)
+            for e, ep in enumerate(epochs):
+                g = ep["steps"][k]
+                assert env.pos[e].cpu().tolist() == g["pos"], (e, k)
+                assert env.assoc[e].cpu().tolist() == g["conn"], (e, k)
+                assert env.rate[e].cpu().tolist() == g["rate"], (e, k)
+                close(env.utility_scaled[e].cpu(), g["utility"], f"epoch {e} step {k}")
+                assert bool(env.done[e]) == g["done"]
+
+
 # --------------------------------------------------------------------- FORK, Philox driven
 @pytest.mark.parametrize("E", [777, 800])  # 777: warp-segment kernel (ragged tail); 800: thread-per-env kernel
 @pytest.mark.parametrize("autoreset", [False, True])

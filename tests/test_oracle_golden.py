@@ -141,3 +141,26 @@ def test_philox_point_is_uniform_int():
     assert x.min() == 0 and x.max() == 199 and y.min() == 0 and y.max() == 199
     h = np.bincount(x, minlength=200)
     assert abs(h - 1000).max() < 200  # ~6 sigma
+
+
+def test_custom_epochs_oracle_matches_reference():
+    """MComCustom as shipped (custom.py): a new BS layout every epoch, the same trajectory."""
+    import json
+    import os
+
+    from conftest import GOLDEN_DIR
+
+    with open(os.path.join(GOLDEN_DIR, "custom_epochs.json")) as f:
+        data = json.load(f)
+    assert len({json.dumps(e["init_pos"]) for e in data["epochs"]}) == 1  # reset_rng_episode=True
+    assert len({json.dumps(e["bs_xy"]) for e in data["epochs"]}) == len(data["epochs"])
+    p = orc.Params(velocity=10)  # MComCustom.default_config (custom.py:13-19)
+    for ep in data["epochs"]:
+        seq = golden_waypoints(ep)
+        env = orc.ScalarEnv(p, ep["bs_xy"], 7, wp_source=lambda u, k: seq[u][k])
+        env.reset(ep["init_pos"])
+        for k, g in enumerate(ep["steps"]):
+            o = env.step_fork()
+            assert [list(q) for q in o["pos"]] == g["pos"] and o["assoc"] == g["conn"], k
+            assert o["rate"] == g["rate"] and o["done"] == g["done"]
+            np.testing.assert_allclose(o["utility"], g["utility"], rtol=1e-12, atol=1e-15)
