@@ -456,7 +456,7 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
     env->launches += 1;
     return 0;
   }
-  if (env->tpe && env->tpe_bound_ok && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr && !a.inj_wp) {
+  if (env->tpe && env->tpe_bound_ok && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr) {
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(a.E / 32);
     lc.blockDim = dim3(32);
@@ -471,7 +471,7 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
     env->launches += 1;
     return 0;
   }
-  if (env->upt && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr && !a.inj_wp) {
+  if (env->upt && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr) {
     a.epb = env->upt_epb;  // envs per CTA of this mapping (bounds and size of the obs bulk store)
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((a.E + a.epb - 1) / a.epb);
@@ -487,8 +487,8 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
     env->launches += 1;
     return 0;
   }
-  // debug SNR output and waypoint injection only exist in the generic kernel
-  if (env->spec && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr && !a.inj_wp)
+  // the debug SNR output only exists in the generic kernel
+  if (env->spec && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr)
   {
     const bool pdl = pdl_enabled();
     cudaLaunchConfig_t lc = {};

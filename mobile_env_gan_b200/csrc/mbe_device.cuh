@@ -145,6 +145,23 @@ __device__ __forceinline__ void unpack_xy(uint32_t p, int& x, int& y) {
   y = (int)(p) >> 16;
 }
 
+// The waypoint a UE without one gets (movement.py:44-47): the next injected one when a replay
+// table is bound (tests replaying reference trajectories), else a Philox draw.
+__device__ __forceinline__ void next_waypoint(const StepArgs& a, unsigned gid, unsigned ue, size_t idx, int t_e,
+                                              int epi, bool valid, int& wx, int& wy) {
+  if (a.inj_wp) {
+    if (valid) {
+      const int k = a.wp_cnt[idx];
+      unpack_xy(a.inj_wp[idx * a.inj_k + min(k, a.inj_k - 1)], wx, wy);
+      a.wp_cnt[idx] = k + 1;
+    } else {
+      wx = wy = 0;
+    }
+  } else {
+    philox_point(a, gid, ue, (unsigned)t_e, P_WAYPOINT, a.reset_rng_episode ? 0u : (unsigned)epi, wx, wy);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // RandomWaypointMovement.move once the waypoint exists (movement.py:49-62).
 // Reference arithmetic (FP64): pos + (velocity * v) / norm(v), np.round (half-even), astype(int).

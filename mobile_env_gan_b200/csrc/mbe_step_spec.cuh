@@ -5,7 +5,7 @@
 // (mbe_step.cuh), which remains the path for reset / observe / split phases and for shapes
 // without an instantiation.  Only the whole fused step (OP_STEP, all phases) runs here.
 // Preconditions checked by the dispatcher (mbe.cu): one BS class, width^2+height^2 < 2^24
-// (squared distances are exact in FP32), no debug SNR output and no waypoint injection bound.
+// (squared distances are exact in FP32), no debug SNR output bound.
 #pragma once
 #include "mbe_device.cuh"
 
@@ -126,8 +126,7 @@ __device__ __forceinline__ void step_chunk(const StepArgs& a, const int env_base
   };
 
   auto phase_move = [&]() {
-    if (wx < 0)  // no waypoint: draw one (movement.py:44-47)
-      philox_point(a, gid, (unsigned)u, (unsigned)t_e, P_WAYPOINT, a.reset_rng_episode ? 0u : (unsigned)epi, wx, wy);
+    if (wx < 0) next_waypoint(a, gid, (unsigned)u, idx, t_e, epi, valid, wx, wy);  // movement.py:44-47
     if (move_ue(a, x, y, wx, wy)) wx = wy = -1;
   };
 

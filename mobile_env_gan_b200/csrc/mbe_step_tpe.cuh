@@ -10,8 +10,8 @@
 // Sums replay the association order of the warp-segment kernels' shuffle tree, so all outputs are
 // bit-identical to them.
 // Preconditions (dispatcher): FORK mode, per-env layout, one BS class, E % 32 == 0, exact-FP32
-// map no larger than 2048 x 2048 (the packed nearest-BS key must not overflow), no debug / injection buffers, all
-// stream bases 16-byte aligned, nbs bound.
+// map no larger than 2048 x 2048 (the packed nearest-BS key must not overflow), no debug SNR buffer, all stream
+// bases 16-byte aligned, nbs bound.
 #pragma once
 #include "mbe_device.cuh"
 #include "mbe_step_spec.cuh"  // mbar_* / bulk_load helpers
@@ -104,8 +104,7 @@ __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant
     int x, y, wx, wy;
     unpack_xy(my_pos[u], x, y);
     unpack_xy(my_wp[u], wx, wy);
-    if (wx < 0)
-      philox_point(a, gid, (unsigned)u, (unsigned)t_e, P_WAYPOINT, a.reset_rng_episode ? 0u : (unsigned)epi, wx, wy);
+    if (wx < 0) next_waypoint(a, gid, (unsigned)u, (size_t)env * U + u, t_e, epi, true, wx, wy);
     if (move_ue(a, x, y, wx, wy)) wx = wy = -1;
     my_pos[u] = pack_xy(x, y);
     my_wp[u] = pack_xy(wx, wy);
@@ -163,6 +162,7 @@ __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant
       philox_point(a, gid, (unsigned)u, 0u, P_INITPOS, a.reset_rng_episode ? 0u : (unsigned)epi, x, y);
       my_pos[u] = pack_xy(x, y);
       my_wp[u] = pack_xy(-1, -1);
+      if (a.inj_wp) a.wp_cnt[(size_t)env * U + u] = 0;
     }
     if (a.bs_rand_max > 0) {  // generate_base_stations (custom.py:68-77)
       nb = philox_bs_count(a, gid, (unsigned)epi);

@@ -201,9 +201,7 @@ __global__ void __launch_bounds__(32 * MBE_UPT_WARPS, MBE_UPT_MIN_BLOCKS(HANDLER
   // ---- move (movement.py:42-62) ----
 #pragma unroll
   for (int j = 0; j < UPT; ++j) {
-    if (wx[j] < 0)
-      philox_point(a, gid, (unsigned)(k + K * j), (unsigned)t_e, P_WAYPOINT, a.reset_rng_episode ? 0u : (unsigned)epi,
-                   wx[j], wy[j]);
+    if (wx[j] < 0) next_waypoint(a, gid, (unsigned)(k + K * j), idx[j], t_e, epi, valid, wx[j], wy[j]);
     if (move_ue(a, x[j], y[j], wx[j], wy[j])) wx[j] = wy[j] = -1;
   }
 
@@ -228,6 +226,7 @@ __global__ void __launch_bounds__(32 * MBE_UPT_WARPS, MBE_UPT_MIN_BLOCKS(HANDLER
     for (int j = 0; j < UPT; ++j) {
       wx[j] = wy[j] = -1;
       philox_point(a, gid, (unsigned)(k + K * j), 0u, P_INITPOS, a.reset_rng_episode ? 0u : (unsigned)epi, x[j], y[j]);
+      if (a.inj_wp) a.wp_cnt[idx[j]] = 0;
     }
     if (k == 0) a.episode[env] = epi;
   }
