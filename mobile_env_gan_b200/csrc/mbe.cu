@@ -445,7 +445,7 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
   if (env->big) {
     if (op == mbe::OP_OBSERVE || (op == mbe::OP_STEP && phases != MBE_PHASE_ALL))
       return fail("split phases / observe are not available on the block-per-env kernel (wide shapes)");
-    if (a.dbg_snr || a.inj_wp) return fail("debug SNR / waypoint injection are not available for wide shapes");
+    if (a.dbg_snr) return fail("the debug SNR output is not available for wide shapes");
     if (!gym)
       mbe::step_big_kernel<0, 0><<<env->grid, mbe::kBigThreads, sizeof(mbe::BigSmem), st>>>(a);
     else if (!ma)

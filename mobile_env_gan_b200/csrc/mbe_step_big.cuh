@@ -127,9 +127,7 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
     for (int i = 0; i < kBigMaxI; ++i) {
       const int u = tid + i * kBigThreads;
       if (u >= U) continue;
-      if (wx[i] < 0)
-        philox_point(a, gid, (unsigned)u, (unsigned)t_e, P_WAYPOINT, a.reset_rng_episode ? 0u : (unsigned)epi,
-                     wx[i], wy[i]);
+      if (wx[i] < 0) next_waypoint(a, gid, (unsigned)u, (size_t)env * U + u, t_e, epi, true, wx[i], wy[i]);
       if (move_ue(a, x[i], y[i], wx[i], wy[i])) wx[i] = wy[i] = -1;
     }
   };
@@ -193,6 +191,7 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
       c0[i] = c1[i] = 0;
       wx[i] = wy[i] = -1;
       philox_point(a, gid, (unsigned)u, 0u, P_INITPOS, a.reset_rng_episode ? 0u : (unsigned)epi, x[i], y[i]);
+      if (a.inj_wp) a.wp_cnt[(size_t)env * U + u] = 0;
     }
     __syncthreads();
   };

@@ -75,6 +75,10 @@ CASES = {
     "long_crawl": ([(60, 60), (140, 60), (60, 140), (140, 140)], 6, ep_cfg(100), 100),
 }
 
+# a wide shape (more than 32 UEs and more than 32 BSs): the block-per-env kernel's territory
+CASES["wide_40x35"] = ([((i * 37 + 11) % 200, (i * 53 + 29) % 200) for i in range(35)], 40,
+                       ep_cfg(12, {"ue": {"velocity": 9}}), 12)
+
 # per-BS radio overrides (BaseStation keyword names): the reference keeps bw/freq/tx/height per BS
 BS_OVERRIDES = {
     "two_classes": {1: {"tx": 30}, 3: {"tx": 30, "bw": 18e6}},
@@ -115,6 +119,9 @@ def main():
             assert [tuple(q) for q in s19["pos"]] == KAT2_POS, s19["pos"]
             got = {(u, b): r for u, b, r in s19["pair_rates"]}
             assert got == KAT2_RATES, got
+        if name.startswith("wide_"):
+            for st in rec["steps"]:
+                st["snr"] = None  # 40 x 35 doubles per step: not needed, the rates pin the chain
         path = os.path.join(OUT, f"fork_{name}.json")
         with open(path, "w") as f:
             json.dump(rec, f, separators=(",", ":"))

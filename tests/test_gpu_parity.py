@@ -82,6 +82,9 @@ def test_fork_replays_reference_trajectory(name, fast):
         assert len(env.plan.classes) > 1
     else:
         env = make_env(rec["bs_xy"], U, golden_config(rec, {"num_envs": E, "mode": "fork"}))
+    wide = U > 32 or len(rec["bs_xy"]) > 32  # block-per-env kernel: no debug SNR output
+    if wide and not fast:
+        pytest.skip("wide shapes have a single kernel (covered by fast=True)")
     snr_dbg = None if fast else env.enable_debug_snr()
     seq = golden_waypoints(rec)
     K = max(1, max(len(s) for s in seq))
