@@ -285,6 +285,44 @@ def main():
         ms = ev0.elapsed_time(ev1)
         gpu_launches = args.steps  # one step_kernel launch per step (graph nodes included)
 
+        # ---- secondary: two env groups in flight (two streams, each its own dependent chain) ----
+        # A single chain of 18 us kernels pays ~3 us of ramp/drain per launch; when the caller
+        # steps two groups of envs alternately (double-buffered actors) the groups' launches
+        # overlap and hide it.  Reported separately; `value` above stays the single-stream number.
+        two = None
+        if not args.no_graph and R >= 2 and not fork:
+            streams2 = [torch.cuda.Stream(device=dev) for _ in range(2)]
+            graphs2, sub = [], 64
+            for si, st2 in enumerate(streams2):
+                mine = [envs[i] for i in range(R) if i % 2 == si]
+                with torch.cuda.stream(st2):
+                    for i in range(len(mine)):
+                        mine[i].step(mine[i].actions)
+                    torch.cuda.synchronize()
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2, stream=st2):
+                        for i in range(sub):
+                            mine[i % len(mine)].step(mine[i % len(mine)].actions)
+                graphs2.append(g2)
+            reps = max(1, args.steps // (2 * sub))
+            for g2, st2 in zip(graphs2, streams2):
+                with torch.cuda.stream(st2):
+                    g2.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for st2 in streams2:
+                st2.wait_event(e0)
+            for _ in range(reps):
+                for g2, st2 in zip(graphs2, streams2):
+                    with torch.cuda.stream(st2):
+                        g2.replay()
+            for st2 in streams2:
+                stream.wait_stream(st2)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            two = (e0.elapsed_time(e1), reps * 2 * sub)
+
         # ---- end to end through the host-buffer ABI call ----
         e2e_steps = max(5, min(args.steps, 40))
         if fork:
@@ -340,10 +378,11 @@ def main():
             torch.cuda.synchronize()
             e2e_lite = (time.perf_counter() - t0, rew_h.numel() * 4 + E)
 
-    times = torch.tensor([ms, e2e_s * 1e3, (e2e_lite[0] if e2e_lite else 0.0) * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms, e2e_s * 1e3, (e2e_lite[0] if e2e_lite else 0.0) * 1e3, two[0] if two else 0.0],
+                         dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, lite_ms = float(times[0]), float(times[1]), float(times[2])
+    ms, e2e_ms, lite_ms, two_ms = (float(t) for t in times)
     if rank == 0:
         peak, peak_src = measured_peak()
         per_launch_s = ms * 1e-3 / args.steps
@@ -375,6 +414,12 @@ def main():
                         "value": world * E * e2e_steps / (lite_ms * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": e2e_lite[1],
                         "note": "same call with obs_host=NULL: actions in, reward+done out"}},
+            "two_env_groups_in_flight": None if not two else {
+                "value": world * E * two[1] / (two_ms * 1e-3), "unit": UNIT, "steps": two[1],
+                "ms_per_step": two_ms / two[1], "streams": 2,
+                "hbm_frac": bpe["layout"] * E / (two_ms * 1e-3 / two[1]) / 1e9 / peak,
+                "note": "throughput when two groups of env batches are stepped concurrently (each group a "
+                        "dependent chain on its own stream); not used for `value` or `roofline`"},
             "gpu_launches": gpu_launches,
             "clocks": sampler.result(),
         }
