@@ -61,6 +61,8 @@ struct mbe_env {
   void (*upt)(mbe::StepArgs) = nullptr;
   size_t upt_smem = 0;
   int upt_epb = 0;
+  int upt_pf = 0, spec_pf = 0;  // L2 prefetch distance (CTAs) of the two kernel families, 0 = off
+  bool pf_bound_ok = false;     // the prefetched streams are 16-byte aligned
   // thread-per-env FORK kernel (per-env layouts, E % 32 == 0, 16-byte aligned buffers)
   void (*tpe)(mbe::StepArgs) = nullptr;
   size_t tpe_smem = 0;
@@ -359,6 +361,21 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     // persistent grid: one full wave of resident CTAs, never more CTAs than chunks
     env->pipe_grid = std::max(1, std::min(a.E / a.epb, per_sm * sms));
   }
+  if (e == cudaSuccess) {
+    // L2 prefetch distance: 0.75 waves of resident CTAs (measured best of 0.25 .. 2 waves on B200,
+    // profiles/README.md); MBE_PREFETCH=0 turns it off, MBE_PREFETCH=n sets the distance in CTAs
+    const char* v = std::getenv("MBE_PREFETCH");
+    const int forced = v ? std::atoi(v) : -1;
+    int sms = 0;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    auto dist = [&](const void* fn, int threads, size_t smem) {
+      int per_sm = 0;
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
+      return forced >= 0 ? forced : per_sm * sms * 3 / 4;
+    };
+    if (env->upt) env->upt_pf = dist((const void*)env->upt, 32 * MBE_UPT_WARPS, env->upt_smem);
+    if (env->spec) env->spec_pf = dist((const void*)env->spec, mbe::kThreads, env->spec_smem);
+  }
   if (e != cudaSuccess) {
     mbe_destroy(env);
     return fail("mbe_create: cudaFuncSetAttribute(%zu B smem): %s", env->smem, cudaGetErrorString(e));
@@ -416,6 +433,8 @@ int mbe_bind(mbe_env* env, const mbe_buffers* b) {
                     (uintptr_t)b->utility | (uintptr_t)b->done | (uintptr_t)b->metrics;
     // bulk async copies need 16-byte aligned global addresses; the FORK thread-per-env kernel also needs nbs
     env->tpe_bound_ok = (all & 15) == 0 && b->nbs != nullptr;
+    uintptr_t pf = (uintptr_t)b->pos | (uintptr_t)b->wp | (uintptr_t)b->conn | (uintptr_t)b->actions;
+    env->pf_bound_ok = (pf & 15) == 0;
   }
   if (!a.bs_per_env) {
     // a shared layout is constant for the life of the binding: fold the coordinates into the
@@ -473,6 +492,7 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
   }
   if (env->upt && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr) {
     a.epb = env->upt_epb;  // envs per CTA of this mapping (bounds and size of the obs bulk store)
+    a.pf_dist = env->pf_bound_ok ? env->upt_pf : 0;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((a.E + a.epb - 1) / a.epb);
     lc.blockDim = dim3(32 * MBE_UPT_WARPS);
@@ -493,6 +513,7 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
     const bool pdl = pdl_enabled();
     cudaLaunchConfig_t lc = {};
     const bool use_pipe = env->pipe != nullptr;
+    a.pf_dist = env->pf_bound_ok ? env->spec_pf : 0;
     lc.gridDim = dim3(use_pipe ? env->pipe_grid : env->grid);
     lc.blockDim = dim3(mbe::kThreads);
     lc.dynamicSmemBytes = use_pipe ? env->pipe_smem : env->spec_smem;

@@ -86,7 +86,31 @@ struct StepArgs {
   int inj_k;
   const uint8_t* reset_mask;
   int obs_bulk_ok;  // obs base is 16B aligned -> whole-block TMA bulk store allowed
+  int pf_dist;      // L2 prefetch distance in CTAs (0 = off; needs 16B aligned pos/wp/conn/actions)
 };
+
+// L2 prefetch (cp.async.bulk.prefetch.L2) of the per-UE state slices of the CTA that runs
+// a.pf_dist CTAs after this one -- about 0.75 waves of resident CTAs, so the slices are in L2
+// when that CTA starts and its first loads do not pay HBM latency.  One thread, 2 (FORK) or 4 (GYM)
+// instructions; slices are EPB*U words, whole CTAs only.
+template <int EPB, int U, bool GYM>
+__device__ __forceinline__ void prefetch_ahead(const StepArgs& a) {
+  if constexpr ((EPB * U) % 4 == 0) {
+    if (a.pf_dist > 0 && threadIdx.x == 0) {
+      const size_t ahead = (size_t)blockIdx.x + (size_t)a.pf_dist;
+      if ((ahead + 1) * EPB <= (size_t)a.E) {
+        constexpr uint32_t bytes = EPB * U * 4;
+        const size_t off = ahead * EPB * U;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.pos + off), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.wp + off), "r"(bytes) : "memory");
+        if (GYM) {
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.conn + off), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.actions + off), "r"(bytes) : "memory");
+        }
+      }
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011): counter-based replacement for the shared PCG64 stream

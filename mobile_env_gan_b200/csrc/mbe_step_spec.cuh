@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(kThreads, MBE_SPEC_MIN_BLOCKS(MODE, HANDLER, B
   // Both are no-ops when the launch does not carry the attribute.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  prefetch_ahead<EPB, U, GYM>(a);
   constexpr size_t OBS_BYTES = (((size_t)(GYM ? EPB * U * F * 4 : 0)) + 15) & ~(size_t)15;
   constexpr size_t BS_BYTES = PER_ENV ? (size_t)EPB * B * 4 : 0;
   ChunkMem m = {};

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(32 * MBE_UPT_WARPS, MBE_UPT_MIN_BLOCKS(HANDLER
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
+  prefetch_ahead<EPB, U, true>(a);
   int g = lane / K;
   int k = lane - g * K;
   const bool in_group = g < EPW;
