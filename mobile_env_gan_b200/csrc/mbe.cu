@@ -71,13 +71,19 @@ struct mbe_env {
 
 namespace {
 
-bool pdl_enabled() {
-  static const bool on = []() {
+// Programmatic dependent launch (the next step's CTAs become resident while this grid drains).
+// Measured on B200 (profiles/README.md): 3% (graph replay) to 10% (plain launches) faster for the
+// UEs-per-thread kernels, slower for the small-shape specialised kernel -> default on for the former
+// only; MBE_PDL=0 turns it off everywhere, MBE_PDL=1 on everywhere.
+int pdl_mode() {
+  static const int mode = []() {
     const char* v = std::getenv("MBE_PDL");
-    return v && v[0] == '1';
+    return !v ? -1 : (v[0] == '1' ? 1 : 0);
   }();
-  return on;
+  return mode;
 }
+bool pdl_enabled() { return pdl_mode() == 1; }
+bool pdl_enabled_upt() { return pdl_mode() != 0; }
 
 struct SpecEntry {
   int mode, handler, U, B, per_env;
@@ -502,7 +508,7 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
-    lc.numAttrs = pdl_enabled() ? 1 : 0;
+    lc.numAttrs = pdl_enabled_upt() ? 1 : 0;
     MBE_CUDA(cudaLaunchKernelEx(&lc, env->upt, a));
     env->launches += 1;
     return 0;

@@ -91,23 +91,31 @@ struct StepArgs {
 
 // L2 prefetch (cp.async.bulk.prefetch.L2) of the per-UE state slices of the CTA that runs
 // a.pf_dist CTAs after this one -- about 0.75 waves of resident CTAs, so the slices are in L2
-// when that CTA starts and its first loads do not pay HBM latency.  One thread, 2 (FORK) or 4 (GYM)
-// instructions; slices are EPB*U words, whole CTAs only.
+// when that CTA starts and its first loads do not pay HBM latency.  CTAs of the first a.pf_dist
+// (nobody runs ahead of them) prefetch their own slices: called before griddepcontrol.wait, that
+// overlaps the drain of the previous grid under programmatic dependent launch (a prefetch returns
+// nothing to the SM and L2 is the point of coherence, so it may run ahead of the dependency).
+// One thread, 2 (FORK) or 4 (GYM) instructions per slice set; slices are EPB*U words, whole CTAs only.
+template <int EPB, int U, bool GYM>
+__device__ __forceinline__ void prefetch_slices(const StepArgs& a, size_t cta) {
+  constexpr uint32_t bytes = EPB * U * 4;
+  const size_t off = cta * EPB * U;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.pos + off), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.wp + off), "r"(bytes) : "memory");
+  if (GYM) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.conn + off), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.actions + off), "r"(bytes) : "memory");
+  }
+}
+
 template <int EPB, int U, bool GYM>
 __device__ __forceinline__ void prefetch_ahead(const StepArgs& a) {
   if constexpr ((EPB * U) % 4 == 0) {
     if (a.pf_dist > 0 && threadIdx.x == 0) {
       const size_t ahead = (size_t)blockIdx.x + (size_t)a.pf_dist;
-      if ((ahead + 1) * EPB <= (size_t)a.E) {
-        constexpr uint32_t bytes = EPB * U * 4;
-        const size_t off = ahead * EPB * U;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.pos + off), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.wp + off), "r"(bytes) : "memory");
-        if (GYM) {
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.conn + off), "r"(bytes) : "memory");
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.actions + off), "r"(bytes) : "memory");
-        }
-      }
+      if ((int)blockIdx.x < a.pf_dist && ((size_t)blockIdx.x + 1) * EPB <= (size_t)a.E)
+        prefetch_slices<EPB, U, GYM>(a, blockIdx.x);
+      if ((ahead + 1) * EPB <= (size_t)a.E) prefetch_slices<EPB, U, GYM>(a, ahead);
     }
   }
 }

@@ -344,8 +344,8 @@ __global__ void __launch_bounds__(kThreads, MBE_SPEC_MIN_BLOCKS(MODE, HANDLER, B
   // grid drains, and (as the dependent) wait for the previous grid's memory before touching state.
   // Both are no-ops when the launch does not carry the attribute.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
   prefetch_ahead<EPB, U, GYM>(a);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   constexpr size_t OBS_BYTES = (((size_t)(GYM ? EPB * U * F * 4 : 0)) + 15) & ~(size_t)15;
   constexpr size_t BS_BYTES = PER_ENV ? (size_t)EPB * B * 4 : 0;
   ChunkMem m = {};

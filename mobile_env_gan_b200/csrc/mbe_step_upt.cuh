@@ -47,9 +47,9 @@ __global__ void __launch_bounds__(32 * MBE_UPT_WARPS, MBE_UPT_MIN_BLOCKS(HANDLER
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  prefetch_ahead<EPB, U, true>(a);
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  prefetch_ahead<EPB, U, true>(a);
   int g = lane / K;
   int k = lane - g * K;
   const bool in_group = g < EPW;
