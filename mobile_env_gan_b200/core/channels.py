@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import math
 from abc import abstractmethod
-from typing import Tuple
+from typing import Dict, Tuple
 
 import numpy as np
 
@@ -49,6 +49,51 @@ class Channel:
         if snr > ue.snr_threshold:
             return bs.bw * np.log2(1 + snr)
         return 0.0
+
+    # ---- coverage outline (rendering helper of the reference, channels.py:30-75, 86-127) ----
+    @classmethod
+    def boundary_collison(cls, theta: float, x0: float, y0: float, width: float, height: float) -> Tuple:
+        """Where the ray leaving (x0, y0) at angle ``theta`` meets the map border (reference spelling
+        and quadrant rules, channels.py:86-127: the candidate crossings are clamped to the map)."""
+        half_pi = 1 / 2 * np.pi
+        t, tq = np.tan(theta), np.tan(theta - half_pi)
+        on_right = (width, t * (width - x0) + y0)
+        on_top = ((-1) * tq * (height - y0) + x0, height)
+        on_left = (0.0, t * (0.0 - x0) + y0)
+        on_bottom = (tq * (y0 - 0.0) + x0, 0.0)
+        axis = {0.0: (width, y0), half_pi: (x0, height), np.pi: (0.0, y0), 3 * half_pi: (x0, 0.0)}
+        if theta in axis:
+            return axis[theta]
+        if 0.0 < theta < half_pi:
+            return np.min((on_right[0], on_top[0], width)), np.min((on_right[1], on_top[1], height))
+        if half_pi < theta < np.pi:
+            return np.max((on_left[0], on_top[0], 0.0)), np.min((on_left[1], on_top[1], height))
+        if np.pi < theta < 3 * half_pi:
+            return np.max((on_left[0], on_bottom[0], 0.0)), np.max((on_left[1], on_bottom[1], 0.0))
+        return np.min((on_right[0], on_bottom[0], width)), np.max((on_right[1], on_bottom[1], 0.0))
+
+    def isoline(self, bs: BaseStation, ue_config: Dict, map_bounds: Tuple, dthresh: float, num: int = 32):
+        """Outline of the area where a UE built from ``ue_config`` gets more than ``dthresh`` from
+        ``bs``: along ``num`` rays the farthest of 100 sample points whose rate exceeds ``dthresh``
+        (reference channels.py:30-75; rate at the integer-truncated sample point like ``ue.point``).
+        Vectorised over the samples of a ray; raises ValueError like the reference when a ray has
+        no such point."""
+        width, height = map_bounds
+        probe = UserEquipment(None, **ue_config)
+        bx, by = int(bs.x), int(bs.y)
+        outline_x, outline_y = [], []
+        for theta in np.linspace(EPSILON, 2 * np.pi, num=num):
+            x1, y1 = self.boundary_collison(theta, bs.x, bs.y, width, height)
+            slope = (y1 - bs.y) / (x1 - bs.x)
+            xs = np.linspace(bs.x, x1, num=100)
+            ys = slope * (xs - bs.x) + bs.y
+            dist = np.hypot(np.trunc(xs) - bx, np.trunc(ys) - by)
+            rates = np.asarray([self.datarate(bs, probe, self.snr_at_distance(bs, probe, float(d))) for d in dist])
+            (hit,) = np.where(rates > dthresh)
+            far = np.max(hit)
+            outline_x.append(xs[far])
+            outline_y.append(ys[far])
+        return tuple(outline_x), tuple(outline_y)
 
     # ---- folding for the device --------------------------------------------------------
     @abstractmethod

@@ -13,6 +13,8 @@ to what the reference's authors saw.
 from __future__ import annotations
 
 import json
+
+import numpy as np
 import os
 import sys
 
@@ -228,7 +230,34 @@ def custom_epochs_golden(epochs=4, steps=20, seed=123):
     print("custom_epochs", epochs, "epochs", [len(e["bs_xy"]) for e in out["epochs"]], "BSs")
 
 
+def isoline_golden():
+    """Coverage outlines from the reference's ``Channel.isoline`` (channels.py:30-75) for the default
+    BS / UE parameters (base.py:117-123); rays that raise in the reference are recorded by exception
+    name.  Target of ``mobile_env_gan_b200.core.channels.Channel.isoline``."""
+    rh.import_reference()
+    from mobile_env.core.channels import OkumuraHata
+    from mobile_env.core.entities import BaseStation
+
+    ue_cfg = dict(velocity=1.5, snr_tr=2e-8, noise=1e-9, height=1.6)
+    cases = []
+    for pos in [(110, 130), (65, 80), (20, 190), (199, 1), (100.5, 77.25), (0, 0)]:
+        for thr in (0.0, 5.0, 30.0, 1e9):
+            for num in (32, 17):
+                case = {"pos": list(pos), "dthresh": thr, "num": num, "bounds": [200, 200]}
+                try:
+                    with np.errstate(all="ignore"):
+                        xs, ys = OkumuraHata().isoline(BaseStation(0, pos, 9e6, 2500, 40, 50), ue_cfg, (200, 200), thr, num)
+                    case["xs"], case["ys"] = [float(v) for v in xs], [float(v) for v in ys]
+                except Exception as exc:  # noqa: BLE001 - the exception type is the recorded behaviour
+                    case["raises"] = type(exc).__name__
+                cases.append(case)
+    with open(os.path.join(OUT, "isoline.json"), "w") as f:
+        json.dump({"ue_config": ue_cfg, "bs": {"bw": 9e6, "freq": 2500, "tx": 40, "height": 50}, "cases": cases}, f)
+    print("isoline:", len(cases), "cases,", sum("raises" in c for c in cases), "raising")
+
+
 if __name__ == "__main__":
     main()
     dump_golden("kat1")
     custom_epochs_golden()
+    isoline_golden()

@@ -214,3 +214,36 @@ def test_handler_spaces_without_a_gpu():
     stations = [BaseStation(0, (1, 1), **cfg["bs"])]
     users = [UserEquipment(0, **cfg["ue"])]
     assert MComCore.build_plan(stations, users, cfg).handler == _lib.HANDLER_MA
+
+
+def test_isoline_matches_reference_golden():
+    """Channel.isoline / boundary_collison (reference channels.py:30-75, 86-127) against outlines the
+    reference produced in the build container (oracle/gen_golden.py:isoline_golden), including the
+    rays on which the reference raises."""
+    import json
+    import os
+
+    import numpy as np
+
+    from mobile_env_gan_b200.core.channels import OkumuraHata
+    from mobile_env_gan_b200.core.entities import BaseStation
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "isoline.json")) as f:
+        gold = json.load(f)
+    ok = 0
+    for case in gold["cases"]:
+        bs = BaseStation(0, tuple(case["pos"]), **gold["bs"])
+        call = lambda: OkumuraHata().isoline(bs, gold["ue_config"], tuple(case["bounds"]), case["dthresh"], case["num"])
+        with np.errstate(all="ignore"):
+            if "raises" in case:
+                try:
+                    call()
+                except Exception as exc:  # noqa: BLE001
+                    assert type(exc).__name__ == case["raises"]
+                else:
+                    raise AssertionError(f"expected {case['raises']} for {case}")
+            else:
+                xs, ys = call()
+                assert list(map(float, xs)) == case["xs"] and list(map(float, ys)) == case["ys"]
+                ok += 1
+    assert ok >= 16
