@@ -158,6 +158,11 @@ int mbe_reset(mbe_env* env, const uint8_t* env_mask, void* stream);
 /* replaces MComCore.step (base.py:230-296): one fused launch over all bound envs */
 int mbe_step(mbe_env* env, void* stream);
 
+/* the same fused step for the envs [first_env, first_env + num_envs) only (first_env a multiple of
+ * 32; envs are independent, base.py:69-79): lets one handle keep several env groups in flight on
+ * different streams (step group A while a policy reads group B's observations) */
+int mbe_step_window(mbe_env* env, int first_env, int num_envs, void* stream);
+
 /* the same step split into phases (MBE_PHASE_* mask), for per-stage parity and profiling */
 int mbe_stage(mbe_env* env, int phase_mask, void* stream);
 
@@ -176,7 +181,9 @@ int mbe_accumulate_qoe(mbe_env* env, float* acc, float threshold, void* stream);
 int64_t mbe_launch_count(const mbe_env* env);
 
 /* Host-buffer convenience: H2D actions, step, D2H obs/reward/done, then synchronises the
- * stream.  Host pointers should be pinned.  NULL pointers are skipped. */
+ * stream.  Host pointers should be pinned.  NULL pointers are skipped.  Large batches with
+ * observations are processed as env windows on two streams so uploads and the step overlap the
+ * download (MBE_HOST_WINDOWS=n overrides the window count). */
 int mbe_step_host(mbe_env* env, const int32_t* actions_host, float* obs_host,
                   float* reward_host, uint8_t* done_host, void* stream);
 

@@ -100,6 +100,7 @@ SYMBOLS = [
     ("mbe_bind", C.c_int, [C.c_void_p, C.POINTER(Buffers)]),
     ("mbe_reset", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("mbe_step", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("mbe_step_window", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("mbe_stage", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("mbe_channel", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("mbe_observe", C.c_int, [C.c_void_p, C.c_void_p]),

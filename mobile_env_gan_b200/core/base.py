@@ -400,6 +400,13 @@ class MComCore:
         # views only: no extra kernels on the step path (truncated aliases the done bytes)
         return self._obs_view(), self.reward, self._terminated, self.done.view(torch.bool), {"metrics": self.metrics}
 
+    def step_window(self, first_env: int, num_envs: int, stream=None):
+        """The fused step for envs ``[first_env, first_env + num_envs)`` only (``mbe_step_window``);
+        actions are read from ``self.actions``, results land in the usual tensors.  ``stream``:
+        a ``torch.cuda.Stream`` (default: the current one) -- windows on different streams overlap."""
+        st = self._stream() if stream is None else C.c_void_p(stream.cuda_stream)
+        _lib.check(self._lib.mbe_step_window(self._handle, int(first_env), int(num_envs), st))
+
     def stage(self, phase_mask: int):
         _lib.check(self._lib.mbe_stage(self._handle, int(phase_mask), self._stream()))
 

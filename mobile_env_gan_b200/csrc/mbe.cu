@@ -67,6 +67,9 @@ struct mbe_env {
   void (*tpe)(mbe::StepArgs) = nullptr;
   size_t tpe_smem = 0;
   bool tpe_bound_ok = false;
+  // mbe_step_host pipeline: second stream + fork/join events (created on first use)
+  cudaStream_t host_stream = nullptr;
+  cudaEvent_t host_fork = nullptr, host_join = nullptr;
 };
 
 namespace {
@@ -394,6 +397,9 @@ void mbe_destroy(mbe_env* env) {
   if (!env) return;
   for (double* p : env->luts) cudaFree(p);
   if (env->d_bs_class) cudaFree(env->d_bs_class);
+  if (env->host_stream) cudaStreamDestroy(env->host_stream);
+  if (env->host_fork) cudaEventDestroy(env->host_fork);
+  if (env->host_join) cudaEventDestroy(env->host_join);
   delete env;
 }
 
@@ -458,13 +464,47 @@ int mbe_bind(mbe_env* env, const mbe_buffers* b) {
   return 0;
 }
 
-static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* stream) {
+// Restricts the launch arguments to the env window [first, first + count): every stream is
+// env-major, so a window is a pointer shift; Philox counters keep using the global env id.
+static void shift_window(mbe::StepArgs& a, bool ma, size_t first, int count) {
+  const size_t U = a.U, MW = (a.B + 31) >> 5;
+  auto adv = [&](auto*& p, size_t n) {
+    if (p) p += n;
+  };
+  adv(a.pos, first * U);
+  adv(a.wp, first * U);
+  adv(a.t, first);
+  adv(a.episode, first);
+  if (a.bs_per_env) adv(a.bs_xy, first * a.B);
+  adv(a.nbs, first);
+  adv(a.conn, first * U * MW);
+  adv(a.assoc, first * U);
+  adv(a.actions, first * U);
+  adv(a.rate, first * U);
+  adv(a.utility, first * U);
+  adv(a.obs, first * U * a.F);
+  adv(a.reward, ma ? first * U : first);
+  adv(a.done, first);
+  adv(a.metrics, first * 4);
+  adv(a.inj_wp, first * U * (size_t)a.inj_k);
+  adv(a.wp_cnt, first * U);
+  a.env_offset += (unsigned)first;
+  a.E = count;
+}
+
+// window_count == 0: all envs; otherwise the full step of envs [window_first, +window_count)
+// (window_first a multiple of 32 keeps every bulk-copy address 16-byte aligned)
+static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* stream, size_t window_first = 0,
+                  int window_count = 0) {
   if (!env) return fail("null handle");
   if (!env->bound) return fail("mbe_bind has not been called");
   mbe::StepArgs a = env->args;
   a.op = op;
   a.phases = phases;
   a.reset_mask = mask;
+  const bool window = window_count > 0;
+  if (window) shift_window(a, env->cfg.handler == MBE_HANDLER_MA && env->cfg.mode == MBE_MODE_GYM, window_first, window_count);
+  const int grid = env->big ? a.E : (a.E + a.epb - 1) / a.epb;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool gym = env->cfg.mode == MBE_MODE_GYM, ma = env->cfg.handler == MBE_HANDLER_MA;
   if (env->big) {
@@ -472,11 +512,11 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
       return fail("split phases / observe are not available on the block-per-env kernel (wide shapes)");
     if (a.dbg_snr) return fail("the debug SNR output is not available for wide shapes");
     if (!gym)
-      mbe::step_big_kernel<0, 0><<<env->grid, mbe::kBigThreads, sizeof(mbe::BigSmem), st>>>(a);
+      mbe::step_big_kernel<0, 0><<<grid, mbe::kBigThreads, sizeof(mbe::BigSmem), st>>>(a);
     else if (!ma)
-      mbe::step_big_kernel<1, 0><<<env->grid, mbe::kBigThreads, sizeof(mbe::BigSmem), st>>>(a);
+      mbe::step_big_kernel<1, 0><<<grid, mbe::kBigThreads, sizeof(mbe::BigSmem), st>>>(a);
     else
-      mbe::step_big_kernel<1, 1><<<env->grid, mbe::kBigThreads, sizeof(mbe::BigSmem), st>>>(a);
+      mbe::step_big_kernel<1, 1><<<grid, mbe::kBigThreads, sizeof(mbe::BigSmem), st>>>(a);
     MBE_CUDA(cudaGetLastError());
     env->launches += 1;
     return 0;
@@ -518,9 +558,9 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
   {
     const bool pdl = pdl_enabled();
     cudaLaunchConfig_t lc = {};
-    const bool use_pipe = env->pipe != nullptr;
+    const bool use_pipe = env->pipe != nullptr && !window;
     a.pf_dist = env->pf_bound_ok ? env->spec_pf : 0;
-    lc.gridDim = dim3(use_pipe ? env->pipe_grid : env->grid);
+    lc.gridDim = dim3(use_pipe ? env->pipe_grid : grid);
     lc.blockDim = dim3(mbe::kThreads);
     lc.dynamicSmemBytes = use_pipe ? env->pipe_smem : env->spec_smem;
     lc.stream = st;
@@ -532,11 +572,11 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
     MBE_CUDA(cudaLaunchKernelEx(&lc, use_pipe ? env->pipe : env->spec, a));
   }
   else if (!gym)
-    mbe::step_kernel<0, 0><<<env->grid, mbe::kThreads, env->smem, st>>>(a);
+    mbe::step_kernel<0, 0><<<grid, mbe::kThreads, env->smem, st>>>(a);
   else if (!ma)
-    mbe::step_kernel<1, 0><<<env->grid, mbe::kThreads, env->smem, st>>>(a);
+    mbe::step_kernel<1, 0><<<grid, mbe::kThreads, env->smem, st>>>(a);
   else
-    mbe::step_kernel<1, 1><<<env->grid, mbe::kThreads, env->smem, st>>>(a);
+    mbe::step_kernel<1, 1><<<grid, mbe::kThreads, env->smem, st>>>(a);
   MBE_CUDA(cudaGetLastError());
   env->launches += 1;
   return 0;
@@ -547,6 +587,15 @@ int mbe_reset(mbe_env* env, const uint8_t* env_mask, void* stream) {
 }
 
 int mbe_step(mbe_env* env, void* stream) { return launch(env, mbe::OP_STEP, MBE_PHASE_ALL, nullptr, stream); }
+
+int mbe_step_window(mbe_env* env, int first_env, int num_envs, void* stream) {
+  if (!env) return fail("null handle");
+  if (env->big) return fail("mbe_step_window: not available on the block-per-env kernel (wide shapes)");
+  if (first_env < 0 || num_envs <= 0 || (long long)first_env + num_envs > env->cfg.num_envs)
+    return fail("mbe_step_window: window [%d, +%d) outside 0..%d", first_env, num_envs, env->cfg.num_envs);
+  if (first_env % 32) return fail("mbe_step_window: first_env must be a multiple of 32 (16-byte aligned slices)");
+  return launch(env, mbe::OP_STEP, MBE_PHASE_ALL, nullptr, stream, (size_t)first_env, num_envs);
+}
 
 int mbe_stage(mbe_env* env, int phase_mask, void* stream) {
   if (phase_mask <= 0 || phase_mask > MBE_PHASE_ALL) return fail("mbe_stage: bad phase mask %d", phase_mask);
@@ -594,21 +643,50 @@ int mbe_step_host(mbe_env* env, const int32_t* actions_host, float* obs_host, fl
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const mbe::StepArgs& a = env->args;
   const bool gym = env->cfg.mode == MBE_MODE_GYM, ma = env->cfg.handler == MBE_HANDLER_MA;
-  const size_t EU = (size_t)a.E * a.U;
-  if (actions_host) {
-    if (!gym) return fail("mbe_step_host: actions only exist in GYM mode");
-    MBE_CUDA(cudaMemcpyAsync(const_cast<int32_t*>(env->bufs.actions), actions_host, EU * 4, cudaMemcpyHostToDevice, st));
+  if (!gym && (actions_host || obs_host || reward_host))
+    return fail("mbe_step_host: actions, obs and reward only exist in GYM mode");
+  // Env windows on two streams: the action upload and the step of window c+1 overlap the result
+  // download of window c (PCIe is full duplex).  Measured on B200 (profiles/README.md): the call is
+  // bound by the observation download (~48 GB/s); 4 windows gain 2% there and cost 13% when no
+  // observations are downloaded -> default 4 with obs_host, 1 without; MBE_HOST_WINDOWS overrides.
+  const char* wv = std::getenv("MBE_HOST_WINDOWS");
+  const int want = wv ? std::max(1, std::atoi(wv)) : (obs_host ? 4 : 1);
+  constexpr int kAlign = 384;  // multiple of every kernel's envs-per-CTA and of 32 (16-byte aligned slices)
+  int windows = env->big ? 1 : std::min(want, std::max(1, a.E / (8 * kAlign)));
+  const int per = ((a.E + windows - 1) / windows + kAlign - 1) / kAlign * kAlign;
+  if (windows > 1 && !env->host_stream) {
+    MBE_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
+    MBE_CUDA(cudaEventCreateWithFlags(&env->host_fork, cudaEventDisableTiming));
+    MBE_CUDA(cudaEventCreateWithFlags(&env->host_join, cudaEventDisableTiming));
   }
-  if (int rc = mbe_step(env, stream)) return rc;
-  if (obs_host) {
-    if (!gym) return fail("mbe_step_host: obs only exists in GYM mode");
-    MBE_CUDA(cudaMemcpyAsync(obs_host, env->bufs.obs, EU * a.F * 4, cudaMemcpyDeviceToHost, st));
+  if (windows > 1) {  // the side stream starts after everything already queued on the caller's stream
+    MBE_CUDA(cudaEventRecord(env->host_fork, st));
+    MBE_CUDA(cudaStreamWaitEvent(env->host_stream, env->host_fork, 0));
   }
-  if (reward_host) {
-    if (!gym) return fail("mbe_step_host: reward only exists in GYM mode");
-    MBE_CUDA(cudaMemcpyAsync(reward_host, env->bufs.reward, (ma ? EU : (size_t)a.E) * 4, cudaMemcpyDeviceToHost, st));
+  const size_t U = a.U;
+  for (int w = 0, first = 0; first < a.E; ++w, first += per) {
+    const int count = std::min(per, a.E - first);
+    cudaStream_t s = (w & 1) ? env->host_stream : st;
+    const size_t fu = (size_t)first * U, cu = (size_t)count * U;
+    if (actions_host)
+      MBE_CUDA(cudaMemcpyAsync(const_cast<int32_t*>(env->bufs.actions) + fu, actions_host + fu, cu * 4,
+                               cudaMemcpyHostToDevice, s));
+    if (int rc = (windows > 1 ? launch(env, mbe::OP_STEP, MBE_PHASE_ALL, nullptr, s, (size_t)first, count)
+                              : launch(env, mbe::OP_STEP, MBE_PHASE_ALL, nullptr, s)))
+      return rc;
+    if (obs_host)
+      MBE_CUDA(cudaMemcpyAsync(obs_host + fu * a.F, env->bufs.obs + fu * a.F, cu * a.F * 4, cudaMemcpyDeviceToHost, s));
+    if (reward_host) {
+      const size_t f = ma ? fu : (size_t)first, c = ma ? cu : (size_t)count;
+      MBE_CUDA(cudaMemcpyAsync(reward_host + f, env->bufs.reward + f, c * 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (done_host)
+      MBE_CUDA(cudaMemcpyAsync(done_host + first, env->bufs.done + first, (size_t)count, cudaMemcpyDeviceToHost, s));
   }
-  if (done_host) MBE_CUDA(cudaMemcpyAsync(done_host, env->bufs.done, (size_t)a.E, cudaMemcpyDeviceToHost, st));
+  if (windows > 1) {
+    MBE_CUDA(cudaEventRecord(env->host_join, env->host_stream));
+    MBE_CUDA(cudaStreamWaitEvent(st, env->host_join, 0));
+  }
   MBE_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

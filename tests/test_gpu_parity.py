@@ -450,6 +450,73 @@ def test_step_host_roundtrip():
     assert torch.equal(obs_h, obs.cpu()) and torch.equal(rew_h, rew.cpu()) and torch.equal(done_h.bool(), trunc.cpu())
 
 
+@pytest.mark.parametrize(
+    "env_id,E",
+    [
+        ("mobile-medium-central-v0", 7000),  # UEs-per-thread kernel, ragged last window
+        ("mobile-medium-ma-v0", 6144),
+        ("mobile-small-central-v0", 9001),  # specialised warp-segment kernel
+        ("mobile-large-ma-v0", 6500),
+    ],
+)
+def test_step_host_windows_match_device_step(env_id, E, monkeypatch):
+    """mbe_step_host can split a batch into env windows on two streams (copy/step overlap), and
+    mbe_step_window steps a sub-range: both must reproduce the single whole-batch launch exactly,
+    over a full episode + autoreset."""
+    import mobile_env_gan_b200 as mbe
+
+    monkeypatch.setenv("MBE_HOST_WINDOWS", "3")
+    a = mbe.make(env_id, num_envs=E, autoreset=True)  # host windows
+    b = mbe.make(env_id, num_envs=E, autoreset=True)  # one launch
+    c = mbe.make(env_id, num_envs=E, autoreset=True)  # explicit windows on two streams
+    a.reset(), b.reset(), c.reset()
+    U, B = a.NUM_USERS, a.NUM_STATIONS
+    ma = "-ma-" in env_id
+    obs_h = torch.empty(tuple(a.obs.shape), dtype=torch.float32).pin_memory()
+    rew_h = torch.empty((E, U) if ma else (E,), dtype=torch.float32).pin_memory()
+    done_h = torch.empty(E, dtype=torch.uint8).pin_memory()
+    gen = torch.Generator().manual_seed(E)
+    first_launches = a.launch_count
+    steps = a.EP_MAX_TIME + 3
+    side = torch.cuda.Stream()
+    cut = (E // 3) // 32 * 32
+    for _ in range(steps):
+        acts = torch.randint(0, B + 1, (E, U), dtype=torch.int32, generator=gen).pin_memory()
+        a.step_host(acts, obs_h, rew_h, done_h)
+        b.step(acts.cuda())
+        c.actions.copy_(acts.cuda())
+        torch.cuda.synchronize()
+        c.step_window(cut, E - cut, stream=side)
+        c.step_window(0, cut)
+        torch.cuda.synchronize()
+        assert torch.equal(obs_h.view(-1), b.obs.cpu().view(-1))
+        assert torch.equal(rew_h.view(-1), b.reward.cpu().view(-1))
+        assert torch.equal(done_h, b.done.cpu())
+        for name in ("pos", "wp", "t", "episode", "conn", "rate", "utility_scaled", "metrics", "obs", "reward", "done"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
+            assert torch.equal(getattr(c, name), getattr(b, name)), name
+    assert a.launch_count - first_launches == min(3, E // 3072) * steps  # windows hold >= 3072 envs
+
+
+def test_step_host_windows_fork_custom(monkeypatch):
+    """Same for the fork's own scenario (thread-per-env FORK kernel, per-env random layouts)."""
+    from mobile_env_gan_b200.scenarios.custom import MComCustom
+
+    monkeypatch.setenv("MBE_HOST_WINDOWS", "2")
+    E = 8192
+    a = MComCustom(config={"num_envs": E, "autoreset": True})
+    b = MComCustom(config={"num_envs": E, "autoreset": True})
+    a.reset(), b.reset()
+    done_h = torch.empty(E, dtype=torch.uint8).pin_memory()
+    for s in range(23):
+        a.step_host(None, None, None, done_h)
+        b.step(0, s)
+        torch.cuda.synchronize()
+        assert torch.equal(done_h, b.done.cpu())
+        for name in ("pos", "wp", "t", "episode", "assoc", "rate", "utility_scaled", "metrics", "bs_xy", "nbs"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
+
+
 # ------------------------------------------------- wide shapes / ProportionalFair (block-per-env)
 WIDE = {
     # name: (B, U, map, scheduler)
