@@ -177,6 +177,22 @@ int mbe_observe(mbe_env* env, void* stream);
  * #q < threshold, #values): the statistics of chooseBaseStation.ipynb cell 5 `qoeValue` */
 int mbe_accumulate_qoe(mbe_env* env, float* acc, float threshold, void* stream);
 
+/* per-step series of a fused episode: DEVICE pointers, any may be NULL; 16-byte aligned */
+typedef struct mbe_rollout_out {
+  int16_t* pos;   /* [T,E,U,2] positions after each step's move (what base.py:298-404 dumps per step) */
+  int32_t* assoc; /* [T,E,U] serving BS or -1 (base.py:236-241) */
+  double* rate;   /* [T,E,U] rounded data rates (base.py:435) */
+  float* utility; /* [T,E,U] scaled utility = QoE (base.py:253-258) */
+} mbe_rollout_out;
+
+/* FORK mode: `steps` consecutive MComCore.step calls (base.py:230-296; the fork's collect loop
+ * `for s in range(20): env.step(e, s)`) in ONE launch -- state stays on chip between the steps.
+ * qoe_acc (f32 [E,4], may be NULL) accumulates the statistics of mbe_accumulate_qoe over all steps;
+ * `out` (may be NULL) receives the per-step series.  After the call the bound buffers hold exactly
+ * what `steps` calls of mbe_step would have left.  Shapes without the fused kernel run the same
+ * episode as a sequence of step launches (same results). */
+int mbe_rollout(mbe_env* env, int steps, float* qoe_acc, float threshold, const mbe_rollout_out* out, void* stream);
+
 /* number of kernel launches this handle has enqueued so far */
 int64_t mbe_launch_count(const mbe_env* env);
 

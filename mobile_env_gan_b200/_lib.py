@@ -90,6 +90,12 @@ class Buffers(C.Structure):
     ]
 
 
+class RolloutOut(C.Structure):
+    """mbe_rollout_out: per-step series [T,E,U] of a fused episode (device pointers, may be NULL)."""
+
+    _fields_ = [("pos", C.c_void_p), ("assoc", C.c_void_p), ("rate", C.c_void_p), ("utility", C.c_void_p)]
+
+
 # every symbol include/mbe.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("mbe_abi_version", C.c_int, []),
@@ -105,6 +111,7 @@ SYMBOLS = [
     ("mbe_channel", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("mbe_observe", C.c_int, [C.c_void_p, C.c_void_p]),
     ("mbe_accumulate_qoe", C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    ("mbe_rollout", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.POINTER(RolloutOut), C.c_void_p]),
     ("mbe_launch_count", C.c_int64, [C.c_void_p]),
     ("mbe_step_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 ]

@@ -400,6 +400,28 @@ class MComCore:
         # views only: no extra kernels on the step path (truncated aliases the done bytes)
         return self._obs_view(), self.reward, self._terminated, self.done.view(torch.bool), {"metrics": self.metrics}
 
+    def rollout(self, steps: int, qoe_acc=None, threshold: float = 0.0, record=()):
+        """FORK mode: ``steps`` consecutive ``step`` calls (the fork's collect loop
+        ``for s in range(20): env.step(e, s)``) through ``mbe_rollout`` -- one launch for the fork's
+        own scenario.  ``qoe_acc``: f32 ``[E,4]`` tensor receiving the layout-score statistics
+        (``scoring.LayoutScorer.acc``); ``record``: names out of ``("pos", "assoc", "rate",
+        "utility")`` whose per-step series ``[T,E,U(,2)]`` are returned in a dict."""
+        if self._needs_reset:
+            raise RuntimeError("call reset() before rollout()")
+        E, U, dev = self.num_envs, self.NUM_USERS, self.device
+        shapes = {"pos": ((steps, E, U, 2), torch.int16), "assoc": ((steps, E, U), torch.int32),
+                  "rate": ((steps, E, U), torch.float64), "utility": ((steps, E, U), torch.float32)}
+        series = {}
+        out = _lib.RolloutOut()
+        for name in record:
+            shape, dt = shapes[name]
+            series[name] = torch.empty(shape, dtype=dt, device=dev)
+            setattr(out, name, series[name].data_ptr())
+        acc = None if qoe_acc is None else C.c_void_p(qoe_acc.data_ptr())
+        _lib.check(self._lib.mbe_rollout(self._handle, int(steps), acc, C.c_float(threshold),
+                                         C.byref(out) if record else None, self._stream()))
+        return series
+
     def step_window(self, first_env: int, num_envs: int, stream=None):
         """The fused step for envs ``[first_env, first_env + num_envs)`` only (``mbe_step_window``);
         actions are read from ``self.actions``, results land in the usual tensors.  ``stream``:

@@ -67,6 +67,8 @@ struct mbe_env {
   void (*tpe)(mbe::StepArgs) = nullptr;
   size_t tpe_smem = 0;
   bool tpe_bound_ok = false;
+  void (*tpe_rollout)(mbe::StepArgs) = nullptr;  // the same kernel looping over the steps of an episode
+  size_t tpe_rollout_smem = 0;
   // mbe_step_host pipeline: second stream + fork/join events (created on first use)
   cudaStream_t host_stream = nullptr;
   cudaEvent_t host_fork = nullptr, host_join = nullptr;
@@ -330,6 +332,8 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
         !(cfg->flags & MBE_FLAG_GENERIC_KERNEL)) {
       env->tpe = mbe::step_tpe_fork_kernel<7, 10>;
       env->tpe_smem = sizeof(mbe::TpeForkSmem<7, 10>);
+      env->tpe_rollout = mbe::step_tpe_fork_kernel<7, 10, true>;
+      env->tpe_rollout_smem = sizeof(mbe::TpeRolloutSmem<7, 10>);
     }
   }
   env->smem = env->big ? 0 : mbe::smem_bytes(gym, ma, a.epb, a.U, a.B, a.F, a.bs_per_env);
@@ -354,6 +358,9 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     e = cudaFuncSetAttribute((const void*)env->upt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->upt_smem);
   if (e == cudaSuccess && env->tpe)
     e = cudaFuncSetAttribute((const void*)env->tpe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->tpe_smem);
+  if (e == cudaSuccess && env->tpe_rollout)
+    e = cudaFuncSetAttribute((const void*)env->tpe_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)env->tpe_rollout_smem);
   if (e == cudaSuccess && env->pipe) {
     // measured slower than the one-chunk-per-CTA kernel on B200 (profiles/README.md): opt-in only
     const char* v = std::getenv("MBE_PIPE");
@@ -631,6 +638,52 @@ int mbe_accumulate_qoe(mbe_env* env, float* acc, float threshold, void* stream) 
       a.utility, reinterpret_cast<float4*>(acc), a.E, a.U, threshold);
   MBE_CUDA(cudaGetLastError());
   env->launches += 1;
+  return 0;
+}
+
+int mbe_rollout(mbe_env* env, int steps, float* qoe_acc, float threshold, const mbe_rollout_out* out, void* stream) {
+  if (!env) return fail("null handle");
+  if (!env->bound) return fail("mbe_bind has not been called");
+  if (env->cfg.mode != MBE_MODE_FORK) return fail("mbe_rollout: FORK mode only (a GYM step needs fresh actions)");
+  if (steps <= 0) return fail("mbe_rollout: steps must be positive");
+  if ((uintptr_t)qoe_acc & 15) return fail("mbe_rollout: qoe_acc must be 16-byte aligned");
+  const mbe_rollout_out none = {};
+  const mbe_rollout_out& o = out ? *out : none;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const mbe::StepArgs& a0 = env->args;
+  const size_t EU = (size_t)a0.E * a0.U;
+  const uintptr_t series = (uintptr_t)o.pos | (uintptr_t)o.assoc | (uintptr_t)o.rate | (uintptr_t)o.utility;
+  if (env->tpe_rollout && env->tpe_bound_ok && !a0.dbg_snr && (series & 15) == 0 && (o.rate == nullptr || a0.rate)) {
+    // fused episode: one launch, state read and written once
+    mbe::StepArgs a = a0;
+    a.op = mbe::OP_STEP;
+    a.phases = MBE_PHASE_ALL;
+    a.reset_mask = nullptr;
+    a.ro_steps = steps;
+    a.qoe_thr = threshold;
+    a.qoe_acc = reinterpret_cast<float4*>(qoe_acc);
+    a.ro_pos = reinterpret_cast<uint32_t*>(o.pos);
+    a.ro_assoc = o.assoc;
+    a.ro_rate = o.rate;
+    a.ro_util = o.utility;
+    mbe::step_tpe_fork_kernel<7, 10, true><<<a.E / 32, 32, env->tpe_rollout_smem, st>>>(a);
+    MBE_CUDA(cudaGetLastError());
+    env->launches += 1;
+    return 0;
+  }
+  // other shapes: the same episode as a sequence of step launches
+  if (o.pos && env->cfg.autoreset)
+    return fail("mbe_rollout: per-step positions with autoreset need the fused kernel (7 UEs, 10 BS slots, per-env layouts)");
+  if (o.rate && !a0.rate) return fail("mbe_rollout: a rate series needs the rate buffer bound");
+  for (int s = 0; s < steps; ++s) {
+    if (int rc = launch(env, mbe::OP_STEP, MBE_PHASE_ALL, nullptr, stream)) return rc;
+    if (qoe_acc)
+      if (int rc = mbe_accumulate_qoe(env, qoe_acc, threshold, stream)) return rc;
+    if (o.pos) MBE_CUDA(cudaMemcpyAsync(o.pos + 2 * EU * s, a0.pos, EU * 4, cudaMemcpyDeviceToDevice, st));
+    if (o.assoc) MBE_CUDA(cudaMemcpyAsync(o.assoc + EU * s, a0.assoc, EU * 4, cudaMemcpyDeviceToDevice, st));
+    if (o.rate) MBE_CUDA(cudaMemcpyAsync(o.rate + EU * s, a0.rate, EU * 8, cudaMemcpyDeviceToDevice, st));
+    if (o.utility) MBE_CUDA(cudaMemcpyAsync(o.utility + EU * s, a0.utility, EU * 4, cudaMemcpyDeviceToDevice, st));
+  }
   return 0;
 }
 

@@ -87,6 +87,15 @@ struct StepArgs {
   const uint8_t* reset_mask;
   int obs_bulk_ok;  // obs base is 16B aligned -> whole-block TMA bulk store allowed
   int pf_dist;      // L2 prefetch distance in CTAs (0 = off; needs 16B aligned pos/wp/conn/actions)
+  // fused episode (mbe_rollout, FORK thread-per-env kernel): steps per launch, score statistics,
+  // optional per-step series [T,E,U]
+  int ro_steps;
+  float qoe_thr;
+  float4* qoe_acc;
+  uint32_t* ro_pos;
+  int32_t* ro_assoc;
+  double* ro_rate;
+  float* ro_util;
 };
 
 // L2 prefetch (cp.async.bulk.prefetch.L2) of the per-UE state slices of the CTA that runs

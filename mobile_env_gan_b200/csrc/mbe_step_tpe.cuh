@@ -9,12 +9,18 @@
 // copies (TMA) -- 6 loads tracked by an mbarrier, 8-11 stores.
 // Sums replay the association order of the warp-segment kernels' shuffle tree, so all outputs are
 // bit-identical to them.
+// ROLLOUT = true is the fused episode (mbe_rollout): the same step repeated a.ro_steps times with the
+// state staying in shared memory / registers between steps -- state is read once and written once
+// per launch; optional per-step outputs (positions after the move, association, rate, QoE:
+// the series behind base.py:298-404's dumps) leave as bulk stores [T,E,U], and the QoE statistics
+// of the layout score (qoe_accumulate_kernel, mbe_step.cuh) accumulate in registers.
 // Preconditions (dispatcher): FORK mode, per-env layout, one BS class, E % 32 == 0, exact-FP32
 // map no larger than 2048 x 2048 (the packed nearest-BS key must not overflow), no debug SNR buffer, all stream
 // bases 16-byte aligned, nbs bound.
 #pragma once
 #include "mbe_device.cuh"
 #include "mbe_step_spec.cuh"  // mbar_* / bulk_load helpers
+#include <type_traits>
 
 namespace mbe {
 
@@ -34,6 +40,26 @@ struct TpeForkSmem {
   alignas(8) uint64_t bar;
 };
 
+template <int U, int B>
+struct TpeRolloutSmem : TpeForkSmem<U, B> {
+  alignas(16) uint32_t pos_out[32 * U];  // positions after the move (the reset below overwrites pos)
+};
+
+// the lane-strided accumulation + shfl_down tree of qoe_accumulate_kernel (mbe_step.cuh) for one env
+// on a thread-local array: lanes >= U hold zeros, lane 0's result after off = 16, 8, 4, 2, 1
+template <int U>
+__device__ __forceinline__ float tree32_sum(const float (&q)[U]) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = i < U ? q[i] : 0.0f;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < off; ++i) v[i] += v[i + off];
+  }
+  return v[0];
+}
+
 // the shuffle tree of seg_sum / seg_sum_head (mbe_device.cuh) replayed on a thread-local array:
 // v[u] += v[u+off] for off = 1, 2, 4, ... where every lane reads pre-step values
 template <int U>
@@ -52,11 +78,12 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
                : "memory");
 }
 
-template <int U, int B>
+template <int U, int B, bool ROLLOUT = false>
 __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  using S = TpeForkSmem<U, B>;
+  using S = typename std::conditional<ROLLOUT, TpeRolloutSmem<U, B>, TpeForkSmem<U, B>>::type;
   static_assert(B <= 16, "per-BS counts are packed 4 bits per BS into 64 bits");
+  static_assert(U <= 32, "the QoE tree replays a 32-lane reduction");
   S& s = *reinterpret_cast<S*>(smem_raw);
   const int lane = threadIdx.x;
   const size_t e0 = (size_t)blockIdx.x * 32;  // first env of this warp
@@ -88,6 +115,16 @@ __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant
   uint32_t* my_bs = s.bs + lane * B;
   int t_e = s.t[lane], epi = s.epi[lane], nb = s.nbs[lane];
 
+  float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (ROLLOUT && a.qoe_acc) acc = a.qoe_acc[env];
+  const int steps = ROLLOUT ? a.ro_steps : 1;
+  const bool ro_out = ROLLOUT && (a.ro_pos || a.ro_assoc || a.ro_rate || a.ro_util);
+#pragma unroll 1
+  for (int step = 0; step < steps; ++step) {
+  if (ro_out && step > 0) {  // the previous step's bulk stores must have read their staging
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+  }
   // absent slots (b >= nb) are parked far outside the map: they can never be the nearest BS
   int bx[B], by[B];
 #pragma unroll
@@ -108,6 +145,7 @@ __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant
     if (move_ue(a, x, y, wx, wy)) wx = wy = -1;
     my_pos[u] = pack_xy(x, y);
     my_wp[u] = pack_xy(wx, wy);
+    if constexpr (ROLLOUT) s.pos_out[lane * U + u] = my_pos[u];
     // nearest BS = min over (d2 << 4 | b): lowest b wins a distance tie like Python's min
     // (base.py:240); with a single BS class it is connectable iff its d2 <= d2max (base.py:212-214)
     int key = 0x7fffffff;
@@ -148,6 +186,17 @@ __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant
     const float nc = (float)nconn;
     reinterpret_cast<float4*>(s.metrics)[lane] = make_float4(nc, nc, usum * a.inv_U, mean_or_zero(rsum, nc));
   }
+  if (ROLLOUT && a.qoe_acc) {  // this step's two-decimal QoE values (base.py:269) into the score statistics
+    float q1[U], q2[U], ql[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float q = rintf(s.util[lane * U + u] * 100.0f) * 0.01f;
+      q1[u] = q;
+      q2[u] = fmaf(q, q, 0.0f);
+      ql[u] = (q < a.qoe_thr) ? 1.0f : 0.0f;
+    }
+    acc = make_float4(acc.x + tree32_sum<U>(q1), acc.y + tree32_sum<U>(q2), acc.z + tree32_sum<U>(ql), acc.w + (float)U);
+  }
 
   // ---- clock, same-step autoreset (base.py:280-291, 407-409; 172-209; custom.py:40-77) ----
   t_e += 1;
@@ -177,6 +226,21 @@ __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant
   s.t[lane] = t_e;
   s.epi[lane] = epi;
   s.nbs[lane] = nb;
+
+  if constexpr (ROLLOUT) if (ro_out) {  // per-step series [T,E,U]
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      const size_t off = ((size_t)step * a.E + e0) * U;
+      if (a.ro_pos) bulk_store(a.ro_pos + off, s.pos_out, EU);
+      if (a.ro_assoc) bulk_store(a.ro_assoc + off, s.assoc, EU);
+      if (a.ro_rate) bulk_store(a.ro_rate + off, s.rate, 2 * EU);
+      if (a.ro_util) bulk_store(a.ro_util + off, s.util, EU);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  }  // steps
+  if (ROLLOUT && a.qoe_acc) a.qoe_acc[env] = acc;
 
   // ---- everything leaves as bulk async stores ----
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -29,6 +29,13 @@ class LayoutScorer:
         _lib.check(env._lib.mbe_accumulate_qoe(env._handle, C.c_void_p(self.acc.data_ptr()),
                                                C.c_float(self.threshold), env._stream()))
 
+    def run_episode(self, steps: int = None, record=()):
+        """One whole episode through ``mbe_rollout`` with the statistics accumulated inside the
+        kernel (one launch for the fork's own scenario) instead of ``step`` + ``update`` per step."""
+        env = self.env
+        return env.rollout(env.plan.ep_time if steps is None else steps, qoe_acc=self.acc,
+                           threshold=self.threshold, record=record)
+
     def result(self):
         """Per-env dict of tensors with the notebook's keys."""
         s1, s2, neg, n = self.acc.unbind(dim=1)

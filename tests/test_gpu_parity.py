@@ -620,6 +620,79 @@ def test_layout_scorer_matches_notebook_formula():
     assert set(idx.cpu().tolist()) <= set(np.argsort(-want)[:12].tolist())
 
 
+@pytest.mark.parametrize("autoreset,steps", [(False, 20), (True, 47), (True, 1)])
+def test_fused_rollout_equals_stepping_custom(autoreset, steps):
+    """mbe_rollout on the fork's own scenario (one launch, state on chip between the steps) against
+    the same number of mbe_step + mbe_accumulate_qoe calls: final state, score statistics and the
+    per-step series must be bit-identical (the stepping path is pinned to the reference above)."""
+    from mobile_env_gan_b200.scenarios import MComCustom
+    from mobile_env_gan_b200.scoring import LayoutScorer
+
+    E = 4096
+    cfg = {"num_envs": E, "autoreset": autoreset}
+    a, b = MComCustom(config=dict(cfg)), MComCustom(config=dict(cfg))
+    sa, sb = LayoutScorer(a, 0.1), LayoutScorer(b, 0.1)
+    a.reset(), b.reset()
+    a.step(0, 0), b.step(0, 0)  # start mid-episode
+    sa.acc.fill_(0.5), sb.acc.fill_(0.5)  # existing statistics are continued
+    before = a.launch_count
+    series = sa.run_episode(steps, record=("pos", "assoc", "rate", "utility"))
+    assert a.launch_count - before == 1
+    for k in range(steps):
+        b.step(0, k)
+        sb.update()
+        torch.cuda.synchronize()
+        assert torch.equal(series["assoc"][k], b.assoc), k
+        assert torch.equal(series["rate"][k], b.rate), k
+        assert torch.equal(series["utility"][k], b.utility_scaled), k
+        if not (autoreset and bool(b.done.any())):  # on a reset step b.pos already holds the new episode
+            assert torch.equal(series["pos"][k], b.pos), k
+    for name in ("pos", "wp", "t", "episode", "assoc", "rate", "utility_scaled", "metrics", "bs_xy", "nbs", "done"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert torch.equal(sa.acc, sb.acc)
+
+
+def test_rollout_positions_on_reset_steps_are_the_moved_ones():
+    """The position series holds the positions after the move (what the reference dumps,
+    base.py:232-233, 298-404) also on the step that ends an episode and auto-resets."""
+    from mobile_env_gan_b200.scenarios import MComCustom
+
+    E = 2048
+    a = MComCustom(config={"num_envs": E, "autoreset": True})
+    b = MComCustom(config={"num_envs": E, "autoreset": False})
+    a.reset(), b.reset()
+    series = a.rollout(20, record=("pos",))
+    for k in range(20):
+        b.step(0, k)
+    assert bool(b.done.all()) and torch.equal(series["pos"][19], b.pos)
+    assert int(a.episode.min()) == 1 and int(a.t.max()) == 0
+
+
+def test_rollout_other_shapes_run_as_step_sequence():
+    """Shapes without the fused kernel: same API, same results, one launch per step."""
+    from mobile_env_gan_b200.scoring import LayoutScorer
+
+    MComCore, BaseStation, UserEquipment = _mods()
+    a = make_env(SCENARIOS["small"][0], 5, {"num_envs": 300})
+    b = make_env(SCENARIOS["small"][0], 5, {"num_envs": 300})
+    sa, sb = LayoutScorer(a), LayoutScorer(b)
+    a.reset(), b.reset()
+    series = sa.run_episode(12, record=("pos", "rate", "assoc", "utility"))
+    for k in range(12):
+        b.step(0, k)
+        sb.update()
+        assert torch.equal(series["pos"][k], b.pos) and torch.equal(series["rate"][k], b.rate)
+        assert torch.equal(series["assoc"][k], b.assoc) and torch.equal(series["utility"][k], b.utility_scaled)
+    assert torch.equal(sa.acc, sb.acc) and torch.equal(a.pos, b.pos) and torch.equal(a.t, b.t)
+    import mobile_env_gan_b200 as mbe
+    from mobile_env_gan_b200._lib import MbeError
+
+    g = mbe.make("mobile-small-central-v0", num_envs=64)
+    g.reset()
+    with pytest.raises(MbeError):
+        g.rollout(3)
+
+
 def test_errors_are_loud():
     MComCore, BaseStation, UserEquipment = _mods()
     from mobile_env_gan_b200._lib import MbeError
