@@ -323,6 +323,27 @@ def main():
             torch.cuda.synchronize()
             two = (e0.elapsed_time(e1), reps * 2 * sub)
 
+        # secondary figure for the fork's own use (collect / layout search: 20 policy-free steps per
+        # epoch, custom.py + chooseBaseStation.ipynb): whole episodes through mbe_rollout, one launch
+        # per episode with the layout-score statistics accumulated in the kernel
+        fused = None
+        if fork:
+            from mobile_env_gan_b200.scoring import LayoutScorer
+
+            scorers = [LayoutScorer(e) for e in envs]
+            T = envs[0].plan.ep_time
+            reps = max(R, args.steps // T)
+            for sc in scorers:
+                sc.run_episode(T)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for r in range(reps):
+                scorers[r % R].run_episode(T)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            fused = (e0.elapsed_time(e1), reps * T, reps)
+
         # ---- end to end through the host-buffer ABI call ----
         e2e_steps = max(5, min(args.steps, 40))
         if fork:
@@ -378,11 +399,11 @@ def main():
             torch.cuda.synchronize()
             e2e_lite = (time.perf_counter() - t0, rew_h.numel() * 4 + E)
 
-    times = torch.tensor([ms, e2e_s * 1e3, (e2e_lite[0] if e2e_lite else 0.0) * 1e3, two[0] if two else 0.0],
-                         dtype=torch.float64, device=dev)
+    times = torch.tensor([ms, e2e_s * 1e3, (e2e_lite[0] if e2e_lite else 0.0) * 1e3, two[0] if two else 0.0,
+                          fused[0] if fused else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, lite_ms, two_ms = (float(t) for t in times)
+    ms, e2e_ms, lite_ms, two_ms, fused_ms = (float(t) for t in times)
     if rank == 0:
         peak, peak_src = measured_peak()
         per_launch_s = ms * 1e-3 / args.steps
@@ -420,6 +441,11 @@ def main():
                 "hbm_frac": bpe["layout"] * E / (two_ms * 1e-3 / two[1]) / 1e9 / peak,
                 "note": "throughput when two groups of env batches are stepped concurrently (each group a "
                         "dependent chain on its own stream); not used for `value` or `roofline`"},
+            "fused_episode": None if not fused else {
+                "value": world * E * fused[1] / (fused_ms * 1e-3), "unit": UNIT, "steps_per_launch": fused[1] // fused[2],
+                "launches": fused[2], "ms_per_launch": fused_ms / fused[2],
+                "note": "mbe_rollout: whole episodes in one launch each with the layout-score statistics "
+                        "accumulated in the kernel; not used for `value` or `roofline`"},
             "gpu_launches": gpu_launches,
             "clocks": sampler.result(),
         }
