@@ -76,10 +76,12 @@ struct mbe_env {
 
 namespace {
 
-// Programmatic dependent launch (the next step's CTAs become resident while this grid drains).
-// Measured on B200 (profiles/README.md): 3% (graph replay) to 10% (plain launches) faster for the
-// UEs-per-thread kernels, slower for the small-shape specialised kernel -> default on for the former
-// only; MBE_PDL=0 turns it off everywhere, MBE_PDL=1 on everywhere.
+// Programmatic dependent launch (the next step's CTAs become resident while this grid drains and
+// prefetch their state slices into L2 before the dependency wait).  Measured on B200
+// (profiles/README.md): 3-7% (graph replay) to 10% (plain launches) faster for the medium GYM
+// kernels, 14% for the small shape, neutral for the large one, 2% slower for the FORK kernels (no
+// prefetch there) -> default on for the GYM step kernels only; MBE_PDL=0 turns it off everywhere,
+// MBE_PDL=1 on everywhere.
 int pdl_mode() {
   static const int mode = []() {
     const char* v = std::getenv("MBE_PDL");
@@ -88,7 +90,7 @@ int pdl_mode() {
   return mode;
 }
 bool pdl_enabled() { return pdl_mode() == 1; }
-bool pdl_enabled_upt() { return pdl_mode() != 0; }
+bool pdl_enabled_gym() { return pdl_mode() != 0; }
 
 struct SpecEntry {
   int mode, handler, U, B, per_env;
@@ -555,7 +557,7 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
-    lc.numAttrs = pdl_enabled_upt() ? 1 : 0;
+    lc.numAttrs = pdl_enabled_gym() ? 1 : 0;
     MBE_CUDA(cudaLaunchKernelEx(&lc, env->upt, a));
     env->launches += 1;
     return 0;
@@ -563,7 +565,7 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
   // the debug SNR output only exists in the generic kernel
   if (env->spec && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr)
   {
-    const bool pdl = pdl_enabled();
+    const bool pdl = gym ? pdl_enabled_gym() : pdl_enabled();
     cudaLaunchConfig_t lc = {};
     const bool use_pipe = env->pipe != nullptr && !window;
     a.pf_dist = env->pf_bound_ok ? env->spec_pf : 0;
