@@ -125,12 +125,31 @@ __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
   }
-  // absent slots (b >= nb) are parked far outside the map: they can never be the nearest BS
-  int bx[B], by[B];
+  // Per-BS terms of key(u, b) = 16 * d2(u, b) + b = cb + mx * x + my * y + 16 * (x^2 + y^2): two
+  // multiply-adds and a min per UE x BS pair; the UE's own term is added after the min.
+  // Absent slots (b >= nb) are parked far outside the map: they can never be the nearest BS.
+  int cb[B], mx[B], my[B];
 #pragma unroll
   for (int b = 0; b < B; ++b) {
-    unpack_xy(my_bs[b], bx[b], by[b]);
-    if (b >= nb) bx[b] = by[b] = -6000;  // 2*(6000+2048)^2 << 4 still fits int32; > any d2max on such a map
+    int bx, by;
+    unpack_xy(my_bs[b], bx, by);
+    if (b >= nb) bx = by = -6000;  // 2*(6000+2048)^2 << 4 still fits int32; > any d2max on such a map
+    cb[b] = ((bx * bx + by * by) << 4) | b;
+    mx[b] = -32 * bx;
+    my[b] = -32 * by;
+  }
+
+  // ---- waypoint draws first (movement.py:44-47): a lane that needs k new waypoints loops k times,
+  // so the warp pays max-over-lanes draws (usually 1-3) instead of one per UE slot ----
+  unsigned need = 0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) need |= ((my_wp[u] >> 15) & 1u) << u;  // x < 0: no waypoint
+  while (need) {
+    const int u = __ffs((int)need) - 1;
+    need &= need - 1;
+    int wx, wy;
+    next_waypoint(a, gid, (unsigned)u, (size_t)env * U + u, t_e, epi, true, wx, wy);
+    my_wp[u] = pack_xy(wx, wy);
   }
 
   // ---- move (movement.py:42-62), then nearest connectable BS (base.py:236-241) ----
@@ -141,7 +160,6 @@ __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant
     int x, y, wx, wy;
     unpack_xy(my_pos[u], x, y);
     unpack_xy(my_wp[u], wx, wy);
-    if (wx < 0) next_waypoint(a, gid, (unsigned)u, (size_t)env * U + u, t_e, epi, true, wx, wy);
     if (move_ue(a, x, y, wx, wy)) wx = wy = -1;
     my_pos[u] = pack_xy(x, y);
     my_wp[u] = pack_xy(wx, wy);
@@ -150,10 +168,8 @@ __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant
     // (base.py:240); with a single BS class it is connectable iff its d2 <= d2max (base.py:212-214)
     int key = 0x7fffffff;
 #pragma unroll
-    for (int b = 0; b < B; ++b) {
-      const int dx = x - bx[b], dy = y - by[b];
-      key = min(key, ((dx * dx + dy * dy) << 4) | b);
-    }
+    for (int b = 0; b < B; ++b) key = min(key, cb[b] + mx[b] * x + my[b] * y);
+    key += (x * x + y * y) << 4;
     const int bd = key >> 4;
     const int bb = (bd <= C0.d2max) ? (key & 15) : -1;
     best[u] = bb;
