@@ -180,6 +180,7 @@ int mbe_accumulate_qoe(mbe_env* env, float* acc, float threshold, void* stream);
 /* per-step series of a fused episode: DEVICE pointers, any may be NULL; 16-byte aligned */
 typedef struct mbe_rollout_out {
   int16_t* pos;   /* [T,E,U,2] positions after each step's move (what base.py:298-404 dumps per step) */
+  int16_t* wp;    /* [T,E,U,2] waypoints after the move; (-1,-1) = arrived this step (movement.py:54-56) */
   int32_t* assoc; /* [T,E,U] serving BS or -1 (base.py:236-241) */
   double* rate;   /* [T,E,U] rounded data rates (base.py:435) */
   float* utility; /* [T,E,U] scaled utility = QoE (base.py:253-258) */

@@ -93,7 +93,8 @@ class Buffers(C.Structure):
 class RolloutOut(C.Structure):
     """mbe_rollout_out: per-step series [T,E,U] of a fused episode (device pointers, may be NULL)."""
 
-    _fields_ = [("pos", C.c_void_p), ("assoc", C.c_void_p), ("rate", C.c_void_p), ("utility", C.c_void_p)]
+    _fields_ = [("pos", C.c_void_p), ("wp", C.c_void_p), ("assoc", C.c_void_p), ("rate", C.c_void_p),
+                ("utility", C.c_void_p)]
 
 
 # every symbol include/mbe.h declares: (name, restype, argtypes)

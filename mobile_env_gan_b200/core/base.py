@@ -404,12 +404,13 @@ class MComCore:
         """FORK mode: ``steps`` consecutive ``step`` calls (the fork's collect loop
         ``for s in range(20): env.step(e, s)``) through ``mbe_rollout`` -- one launch for the fork's
         own scenario.  ``qoe_acc``: f32 ``[E,4]`` tensor receiving the layout-score statistics
-        (``scoring.LayoutScorer.acc``); ``record``: names out of ``("pos", "assoc", "rate",
+        (``scoring.LayoutScorer.acc``); ``record``: names out of ``("pos", "wp", "assoc", "rate",
         "utility")`` whose per-step series ``[T,E,U(,2)]`` are returned in a dict."""
         if self._needs_reset:
             raise RuntimeError("call reset() before rollout()")
         E, U, dev = self.num_envs, self.NUM_USERS, self.device
-        shapes = {"pos": ((steps, E, U, 2), torch.int16), "assoc": ((steps, E, U), torch.int32),
+        shapes = {"pos": ((steps, E, U, 2), torch.int16), "wp": ((steps, E, U, 2), torch.int16),
+                  "assoc": ((steps, E, U), torch.int32),
                   "rate": ((steps, E, U), torch.float64), "utility": ((steps, E, U), torch.float32)}
         series = {}
         out = _lib.RolloutOut()

@@ -654,7 +654,7 @@ int mbe_rollout(mbe_env* env, int steps, float* qoe_acc, float threshold, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const mbe::StepArgs& a0 = env->args;
   const size_t EU = (size_t)a0.E * a0.U;
-  const uintptr_t series = (uintptr_t)o.pos | (uintptr_t)o.assoc | (uintptr_t)o.rate | (uintptr_t)o.utility;
+  const uintptr_t series = (uintptr_t)o.pos | (uintptr_t)o.wp | (uintptr_t)o.assoc | (uintptr_t)o.rate | (uintptr_t)o.utility;
   if (env->tpe_rollout && env->tpe_bound_ok && !a0.dbg_snr && (series & 15) == 0 && (o.rate == nullptr || a0.rate)) {
     // fused episode: one launch, state read and written once
     mbe::StepArgs a = a0;
@@ -665,6 +665,7 @@ int mbe_rollout(mbe_env* env, int steps, float* qoe_acc, float threshold, const 
     a.qoe_thr = threshold;
     a.qoe_acc = reinterpret_cast<float4*>(qoe_acc);
     a.ro_pos = reinterpret_cast<uint32_t*>(o.pos);
+    a.ro_wp = reinterpret_cast<uint32_t*>(o.wp);
     a.ro_assoc = o.assoc;
     a.ro_rate = o.rate;
     a.ro_util = o.utility;
@@ -674,7 +675,7 @@ int mbe_rollout(mbe_env* env, int steps, float* qoe_acc, float threshold, const 
     return 0;
   }
   // other shapes: the same episode as a sequence of step launches
-  if (o.pos && env->cfg.autoreset)
+  if ((o.pos || o.wp) && env->cfg.autoreset)
     return fail("mbe_rollout: per-step positions with autoreset need the fused kernel (7 UEs, 10 BS slots, per-env layouts)");
   if (o.rate && !a0.rate) return fail("mbe_rollout: a rate series needs the rate buffer bound");
   for (int s = 0; s < steps; ++s) {
@@ -682,6 +683,7 @@ int mbe_rollout(mbe_env* env, int steps, float* qoe_acc, float threshold, const 
     if (qoe_acc)
       if (int rc = mbe_accumulate_qoe(env, qoe_acc, threshold, stream)) return rc;
     if (o.pos) MBE_CUDA(cudaMemcpyAsync(o.pos + 2 * EU * s, a0.pos, EU * 4, cudaMemcpyDeviceToDevice, st));
+    if (o.wp) MBE_CUDA(cudaMemcpyAsync(o.wp + 2 * EU * s, a0.wp, EU * 4, cudaMemcpyDeviceToDevice, st));
     if (o.assoc) MBE_CUDA(cudaMemcpyAsync(o.assoc + EU * s, a0.assoc, EU * 4, cudaMemcpyDeviceToDevice, st));
     if (o.rate) MBE_CUDA(cudaMemcpyAsync(o.rate + EU * s, a0.rate, EU * 8, cudaMemcpyDeviceToDevice, st));
     if (o.utility) MBE_CUDA(cudaMemcpyAsync(o.utility + EU * s, a0.utility, EU * 4, cudaMemcpyDeviceToDevice, st));

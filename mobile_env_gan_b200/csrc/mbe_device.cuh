@@ -93,6 +93,7 @@ struct StepArgs {
   float qoe_thr;
   float4* qoe_acc;
   uint32_t* ro_pos;
+  uint32_t* ro_wp;
   int32_t* ro_assoc;
   double* ro_rate;
   float* ro_util;

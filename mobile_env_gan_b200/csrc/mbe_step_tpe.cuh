@@ -43,6 +43,7 @@ struct TpeForkSmem {
 template <int U, int B>
 struct TpeRolloutSmem : TpeForkSmem<U, B> {
   alignas(16) uint32_t pos_out[32 * U];  // positions after the move (the reset below overwrites pos)
+  alignas(16) uint32_t wp_out[32 * U];   // waypoints after the move ((-1,-1): arrived this step, movement.py:54-56)
 };
 
 // the lane-strided accumulation + shfl_down tree of qoe_accumulate_kernel (mbe_step.cuh) for one env
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant
   float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   if (ROLLOUT && a.qoe_acc) acc = a.qoe_acc[env];
   const int steps = ROLLOUT ? a.ro_steps : 1;
-  const bool ro_out = ROLLOUT && (a.ro_pos || a.ro_assoc || a.ro_rate || a.ro_util);
+  const bool ro_out = ROLLOUT && (a.ro_pos || a.ro_wp || a.ro_assoc || a.ro_rate || a.ro_util);
 #pragma unroll 1
   for (int step = 0; step < steps; ++step) {
   if (ro_out && step > 0) {  // the previous step's bulk stores must have read their staging
@@ -163,7 +164,10 @@ __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant
     if (move_ue(a, x, y, wx, wy)) wx = wy = -1;
     my_pos[u] = pack_xy(x, y);
     my_wp[u] = pack_xy(wx, wy);
-    if constexpr (ROLLOUT) s.pos_out[lane * U + u] = my_pos[u];
+    if constexpr (ROLLOUT) {
+      s.pos_out[lane * U + u] = my_pos[u];
+      s.wp_out[lane * U + u] = my_wp[u];
+    }
     // nearest BS = min over (d2 << 4 | b): lowest b wins a distance tie like Python's min
     // (base.py:240); with a single BS class it is connectable iff its d2 <= d2max (base.py:212-214)
     int key = 0x7fffffff;
@@ -249,6 +253,7 @@ __global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant
     if (lane == 0) {
       const size_t off = ((size_t)step * a.E + e0) * U;
       if (a.ro_pos) bulk_store(a.ro_pos + off, s.pos_out, EU);
+      if (a.ro_wp) bulk_store(a.ro_wp + off, s.wp_out, EU);
       if (a.ro_assoc) bulk_store(a.ro_assoc + off, s.assoc, EU);
       if (a.ro_rate) bulk_store(a.ro_rate + off, s.rate, 2 * EU);
       if (a.ro_util) bulk_store(a.ro_util + off, s.util, EU);

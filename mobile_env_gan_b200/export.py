@@ -175,6 +175,17 @@ class ReferenceDumpWriter:
         self.q.put(("step", step, sl))
         self.step_count += 1
 
+    def write_rollout(self, series):
+        """A whole episode at once: ``series = env.rollout(T, record=("pos", "wp", "assoc", "rate"))``
+        (one launch for the fork's own scenario) instead of ``after_step`` per step.  Call
+        ``begin_episode()`` before the rollout (it snapshots the BS layouts) and ``end_episode()`` after."""
+        missing = [n for n in ("pos", "wp", "assoc", "rate") if n not in series]
+        if missing:
+            raise ValueError(f"write_rollout needs the series {missing}: record=('pos', 'wp', 'assoc', 'rate')")
+        host = {n: series[n][:, self.sel].cpu().numpy() for n in ("pos", "wp", "assoc", "rate")}
+        self.q.put(("rollout", self.step_count, host))
+        self.step_count += host["pos"].shape[0]
+
     def end_episode(self):
         self.q.put(("epoch", None, None))
         self.q.join()
@@ -215,6 +226,18 @@ class ReferenceDumpWriter:
                     if self.per_step:
                         for i, e in enumerate(self.ids):
                             self._write(format_step_files(e, step, self.bs[i], pos[i], assoc[i], rate[i], self.util_params))
+                elif kind == "rollout":
+                    host, sl = sl, None
+                    for t in range(host["pos"].shape[0]):
+                        pos, assoc, rate = host["pos"][t], host["assoc"][t], host["rate"][t]
+                        self.history["pos"].append(pos)
+                        self.history["arrived"].append(host["wp"][t][:, :, 0] < 0)
+                        self.history["assoc"].append(assoc)
+                        self.history["rate"].append(rate)
+                        if self.per_step:
+                            for i, e in enumerate(self.ids):
+                                self._write(format_step_files(e, step + t, self.bs[i], pos[i], assoc[i], rate[i],
+                                                              self.util_params))
                 elif kind == "epoch":
                     h = self.history
                     for i, e in enumerate(self.ids):

@@ -63,7 +63,8 @@ def test_formatters_reproduce_reference_dump_files_byte_for_byte():
 
 
 @pytest.mark.gpu
-def test_gpu_writer_reproduces_reference_dump_files(tmp_path):
+@pytest.mark.parametrize("how", ["steps", "rollout"])
+def test_gpu_writer_reproduces_reference_dump_files(tmp_path, how):
     import torch
 
     from mobile_env_gan_b200.core.base import MComCore
@@ -90,9 +91,12 @@ def test_gpu_writer_reproduces_reference_dump_files(tmp_path):
     env.set_positions(np.broadcast_to(np.array(rec["init_pos"]), (E, U, 2)).copy())
     writer = ReferenceDumpWriter(env, str(tmp_path), envs=[0, 5])  # env index plays the epoch number
     writer.begin_episode()
-    for s in range(len(rec["steps"])):
-        env.step(0, s)
-        writer.after_step(s)
+    if how == "steps":
+        for s in range(len(rec["steps"])):
+            env.step(0, s)
+            writer.after_step(s)
+    else:  # the whole episode through mbe_rollout, files from its per-step series
+        writer.write_rollout(env.rollout(len(rec["steps"]), record=("pos", "wp", "assoc", "rate")))
     writer.end_episode()
     writer.close()
     files = {}
@@ -123,3 +127,36 @@ def test_gpu_writer_reproduces_reference_dump_files(tmp_path):
     # env 5 ran the same episode: identical contents under its own epoch number
     for rel, text in epoch0.items():
         assert files[with_epoch(rel, 5)] == text
+
+
+@pytest.mark.gpu
+def test_gpu_writer_rollout_equals_stepping_on_custom_scenario(tmp_path):
+    """The fork's own scenario: dump files written from ONE fused-episode launch are the files the
+    per-step path writes (which the test above pins to the reference's own files)."""
+    from mobile_env_gan_b200.export import ReferenceDumpWriter
+    from mobile_env_gan_b200.scenarios.custom import MComCustom
+
+    def run(root, fused):
+        env = MComCustom(config={"num_envs": 64})
+        env.reset()
+        writer = ReferenceDumpWriter(env, str(root), envs=[0, 33, 63])
+        writer.begin_episode()
+        if fused:
+            before = env.launch_count
+            writer.write_rollout(env.rollout(20, record=("pos", "wp", "assoc", "rate")))
+            assert env.launch_count - before == 1
+        else:
+            for s in range(20):
+                env.step(0, s)
+                writer.after_step(s)
+        writer.end_episode()
+        writer.close()
+        out = {}
+        for dirpath, _, names in os.walk(root):
+            for name in names:
+                full = os.path.join(dirpath, name)
+                out[os.path.relpath(full, root)] = open(full).read()
+        return out
+
+    a, b = run(tmp_path / "steps", False), run(tmp_path / "fused", True)
+    assert len(a) == 3 * 84 and a == b

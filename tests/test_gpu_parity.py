@@ -158,6 +158,49 @@ def test_custom_scenario_epochs_replay_reference():
                 assert bool(env.done[e]) == g["done"]
 
 
+def test_custom_scenario_epochs_replay_reference_in_one_launch():
+    """The same reference epochs through mbe_rollout: each whole 20-step epoch of the reference is
+    ONE launch; the per-step series must be the reference's positions / association / FP64 rates."""
+    import json
+    import os
+
+    from conftest import GOLDEN_DIR
+    from mobile_env_gan_b200.scenarios import MComCustom
+
+    with open(os.path.join(GOLDEN_DIR, "custom_epochs.json")) as f:
+        epochs = json.load(f)["epochs"]
+    U, B, REP = 7, 10, 8
+    epochs = [ep for ep in epochs for _ in range(REP)]
+    E, T = len(epochs), len(epochs[0]["steps"])
+    env = MComCustom(config={"num_envs": E})
+    env.reset()
+    bs = np.zeros((E, B, 2), dtype=np.int16)
+    nbs = np.zeros(E, dtype=np.int32)
+    seqs = [golden_waypoints(ep) for ep in epochs]
+    K = max(len(s) for seq in seqs for s in seq)
+    wp = np.zeros((E, U, K, 2), dtype=np.int16)
+    for e, ep in enumerate(epochs):
+        nbs[e] = len(ep["bs_xy"])
+        bs[e, : nbs[e]] = ep["bs_xy"]
+        for u, s in enumerate(seqs[e]):
+            for k, w in enumerate(s):
+                wp[e, u, k] = w
+    env.set_station_positions(bs, nbs)
+    env.inject_waypoints(wp)
+    env.set_positions(np.array([ep["init_pos"] for ep in epochs]))
+    before = env.launch_count
+    series = env.rollout(T, record=("pos", "assoc", "rate", "utility"))
+    assert env.launch_count - before == 1
+    pos, assoc, rate, util = (series[n].cpu() for n in ("pos", "assoc", "rate", "utility"))
+    for e, ep in enumerate(epochs):
+        for k, g in enumerate(ep["steps"]):
+            assert pos[k, e].tolist() == g["pos"], (e, k)
+            assert assoc[k, e].tolist() == g["conn"], (e, k)
+            assert rate[k, e].tolist() == g["rate"], (e, k)  # FP64, bit-exact
+            close(util[k, e], g["utility"], f"epoch {e} step {k}")
+    assert bool(env.done.all())
+
+
 # --------------------------------------------------------------------- FORK, Philox driven
 @pytest.mark.parametrize("E", [777, 800])  # 777: warp-segment kernel (ragged tail); 800: thread-per-env kernel
 @pytest.mark.parametrize("autoreset", [False, True])
