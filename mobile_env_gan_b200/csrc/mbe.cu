@@ -495,6 +495,7 @@ static void shift_window(mbe::StepArgs& a, bool ma, size_t first, int count) {
   adv(a.reward, ma ? first * U : first);
   adv(a.done, first);
   adv(a.metrics, first * 4);
+  adv(a.dbg_snr, first * U * a.B);
   adv(a.inj_wp, first * U * (size_t)a.inj_k);
   adv(a.wp_cnt, first * U);
   a.env_offset += (unsigned)first;
