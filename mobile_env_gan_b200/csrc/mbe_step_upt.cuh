@@ -13,9 +13,10 @@
 #pragma once
 #include "mbe_device.cuh"
 
-// resident CTAs per SM (register budget), tuned on B200: central 8 (64 regs), multi-agent 7 (73 regs)
+// resident CTAs per SM x 2 (register budget), tuned on B200: 7 for both handlers (72 registers, no
+// forced cap; 8 = 64 registers was best before the L2 prefetch, 3.5% slower with it)
 #ifndef MBE_UPT_BLOCKS_SMALL
-#define MBE_UPT_BLOCKS_SMALL 8
+#define MBE_UPT_BLOCKS_SMALL 7
 #endif
 #define MBE_UPT_MIN_BLOCKS(HANDLER, B) ((B) <= 4 ? ((HANDLER) == 1 ? 7 : MBE_UPT_BLOCKS_SMALL) : 6)
 // warps per CTA of this mapping: 2 measured best (finer CTA granularity; 1 would break the 16-byte
