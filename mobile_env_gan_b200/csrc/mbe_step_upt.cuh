@@ -18,7 +18,10 @@
 #ifndef MBE_UPT_BLOCKS_SMALL
 #define MBE_UPT_BLOCKS_SMALL 7
 #endif
-#define MBE_UPT_MIN_BLOCKS(HANDLER, B) ((B) <= 4 ? ((HANDLER) == 1 ? 7 : MBE_UPT_BLOCKS_SMALL) : 6)
+#ifndef MBE_UPT_BLOCKS_MA
+#define MBE_UPT_BLOCKS_MA 7
+#endif
+#define MBE_UPT_MIN_BLOCKS(HANDLER, B) ((B) <= 4 ? ((HANDLER) == 1 ? MBE_UPT_BLOCKS_MA : MBE_UPT_BLOCKS_SMALL) : 6)
 // warps per CTA of this mapping: 2 measured best (finer CTA granularity; 1 would break the 16-byte
 // size rule of the observation bulk store for U=15)
 #ifndef MBE_UPT_WARPS
