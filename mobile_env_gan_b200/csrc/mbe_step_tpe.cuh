@@ -47,16 +47,19 @@ struct TpeRolloutSmem : TpeForkSmem<U, B> {
 };
 
 // the lane-strided accumulation + shfl_down tree of qoe_accumulate_kernel (mbe_step.cuh) for one env
-// on a thread-local array: lanes >= U hold zeros, lane 0's result after off = 16, 8, 4, 2, 1
+// on a thread-local array: lane 0's result after off = 16, 8, 4, 2, 1 with zeros in lanes >= U.
+// Adding those zeros only ever turns a -0 into +0, which no later sum can see, so they are skipped.
 template <int U>
 __device__ __forceinline__ float tree32_sum(const float (&q)[U]) {
-  float v[32];
+  constexpr int P = U <= 1 ? 1 : U <= 2 ? 2 : U <= 4 ? 4 : U <= 8 ? 8 : U <= 16 ? 16 : 32;
+  float v[P];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = i < U ? q[i] : 0.0f;
+  for (int i = 0; i < P; ++i) v[i] = i < U ? q[i] : 0.0f;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
+  for (int off = P / 2; off > 0; off >>= 1) {
 #pragma unroll
-    for (int i = 0; i < off; ++i) v[i] += v[i + off];
+    for (int i = 0; i < off; ++i)
+      if (i + off < U) v[i] += v[i + off];
   }
   return v[0];
 }
@@ -79,8 +82,16 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
                : "memory");
 }
 
+// resident one-warp CTAs per SM the register allocation is held to (step / fused episode)
+#ifndef MBE_TPE_BLOCKS
+#define MBE_TPE_BLOCKS 20
+#endif
+#ifndef MBE_TPE_ROLLOUT_BLOCKS
+#define MBE_TPE_ROLLOUT_BLOCKS 16
+#endif
+
 template <int U, int B, bool ROLLOUT = false>
-__global__ void __launch_bounds__(32) step_tpe_fork_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(32, ROLLOUT ? MBE_TPE_ROLLOUT_BLOCKS : MBE_TPE_BLOCKS) step_tpe_fork_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using S = typename std::conditional<ROLLOUT, TpeRolloutSmem<U, B>, TpeForkSmem<U, B>>::type;
   static_assert(B <= 16, "per-BS counts are packed 4 bits per BS into 64 bits");
