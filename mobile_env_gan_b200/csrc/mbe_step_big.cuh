@@ -373,13 +373,23 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
       float* gbase = a.obs + ((size_t)env * U + u0) * F;
       const int nrows = min(32, U - u0);
       // transposed write-back of tile columns [c0, c0 + n) to feature columns [f0, f0 + n)
+      // (full 32-row tiles of the BASELINE synthetic shape, F = 129 / 257, unroll completely with the
+      // row stride as an immediate: one shared load + one store per row, no address arithmetic)
       auto flush = [&](int f0, int c0_, int n) {
         __syncwarp();
         if (lane < n) {
           float* g = gbase + f0 + lane;
           const float* t = &tile[0][c0_ + lane];
+          if (nrows == 32 && F == 129) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) g[r * 129] = t[r * (kBigMaxB + 1)];
+          } else if (nrows == 32 && F == 257) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) g[r * 257] = t[r * (kBigMaxB + 1)];
+          } else {
 #pragma unroll 8
-          for (int r = 0; r < nrows; ++r) g[(size_t)r * F] = t[r * (kBigMaxB + 1)];
+            for (int r = 0; r < nrows; ++r) g[(size_t)r * F] = t[r * (kBigMaxB + 1)];
+          }
         }
         __syncwarp();
       };
