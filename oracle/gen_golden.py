@@ -81,6 +81,16 @@ CASES = {
 CASES["wide_40x35"] = ([((i * 37 + 11) % 200, (i * 53 + 29) % 200) for i in range(35)], 40,
                        ep_cfg(12, {"ue": {"velocity": 9}}), 12)
 
+# movement corner cases: v = 2.5 gives exact .5 rounding ties on axis-aligned legs (np.round half-even,
+# movement.py:60); v = 0.4 rounds most steps to no move at all; v = 150 snaps to every waypoint at once
+CASES["v2p5_ties"] = ([(50, 50), (150, 50), (100, 150)], 10, ep_cfg(60, {"ue": {"velocity": 2.5}}), 60)
+CASES["v0p4_crawl"] = ([(50, 50), (150, 50), (100, 150)], 6, ep_cfg(40, {"ue": {"velocity": 0.4}}), 40)
+CASES["v150_teleport"] = ([(50, 50), (150, 50), (100, 150), (20, 180)], 8, ep_cfg(30, {"ue": {"velocity": 150}}), 30)
+# non-default utility curve and receiver: w1*log(w2 + r)/log(w3) clipped to [-5, 25] (utilities.py:44-55)
+CASES["utility_custom"] = ([(60, 60), (140, 60), (60, 140), (140, 140)], 9,
+                           ep_cfg(25, {"ue": {"velocity": 6, "snr_tr": 1e-7, "noise": 5e-10},
+                                       "utility_params": {"lower": -5, "upper": 25, "coeffs": (3, 1, 2)}}), 25)
+
 # per-BS radio overrides (BaseStation keyword names): the reference keeps bw/freq/tx/height per BS
 BS_OVERRIDES = {
     "two_classes": {1: {"tx": 30}, 3: {"tx": 30, "bw": 18e6}},
@@ -90,6 +100,8 @@ CASES["two_classes"] = ([(50, 50), (150, 50), (50, 150), (150, 150), (100, 100)]
 
 
 def main():
+    # NOTE: re-running changes `mean_datarate` of existing files in the last ulp (the reference sums a
+    # dict whose iteration order depends on object hashes); tests compare that field with a tolerance.
     os.makedirs(OUT, exist_ok=True)
     for name, (bs_xy, nue, cfg, steps) in CASES.items():
         over = BS_OVERRIDES.get(name)
