@@ -48,6 +48,8 @@ class Monitor:
             df = pd.DataFrame.from_dict(rows, orient="index")
             if len(df):
                 df.index = pd.MultiIndex.from_tuples(df.index, names=["Time Step", id_name])
+                df = df.sort_index()[sorted(df.columns)]
+            df.columns.name = "Metric"
             return df
 
         return scalar, frame(self.ue_results, "UE ID"), frame(self.bs_results, "BS ID")

@@ -247,3 +247,44 @@ def test_isoline_matches_reference_golden():
                 assert list(map(float, xs)) == case["xs"] and list(map(float, ys)) == case["ys"]
                 ok += 1
     assert ok >= 16
+
+
+def test_monitor_frames_match_reference_monitor():
+    """Monitor.load_results / info (reference logging.py:6-87): same frames as the reference's Monitor
+    fed the same per-step values (env 3 of a batch of 5)."""
+    import pandas as pd
+    import torch
+
+    from oracle import ref_harness
+
+    if not ref_harness.reference_available():
+        pytest.skip("the reference is only importable in the build container")
+    ref_harness.import_reference()
+    from mobile_env.core.logging import Monitor as RefMonitor
+
+    from mobile_env_gan_b200.core.logging import Monitor
+
+    E, U, B, T, env = 5, 4, 3, 6, 3
+    gen = torch.Generator().manual_seed(0)
+    scal = [torch.rand(E, generator=gen, dtype=torch.float64) for _ in range(T)]
+    ue = [torch.rand(E, U, generator=gen, dtype=torch.float64) for _ in range(T)]
+    bs = [torch.rand(E, B, generator=gen, dtype=torch.float64) for _ in range(T)]
+    clock = {"t": 0}
+    mine = Monitor({"mean utility": lambda sim: scal[clock["t"]]}, {"rate": lambda sim: ue[clock["t"]],
+                                                                    "qoe": lambda sim: 2 * ue[clock["t"]]},
+                   {"load": lambda sim: bs[clock["t"]]})
+    ref = RefMonitor({"mean utility": lambda sim: float(scal[clock["t"]][env])},
+                     {"rate": lambda sim: dict(enumerate(ue[clock["t"]][env].tolist())),
+                      "qoe": lambda sim: dict(enumerate((2 * ue[clock["t"]][env]).tolist()))},
+                     {"load": lambda sim: dict(enumerate(bs[clock["t"]][env].tolist()))})
+    mine.reset(), ref.reset()
+    assert mine.info(env) == {} and ref.info() == {}
+    for t in range(T):
+        clock["t"] = t
+        mine.update(None), ref.update(None)
+    got, want = mine.load_results(env), ref.load_results()
+    for g, w in zip(got, want):
+        pd.testing.assert_frame_equal(g, w[sorted(w.columns)] if w.columns.name == "Metric" else w, check_dtype=False)
+    gi, wi = mine.info(env), ref.info()
+    assert gi["mean utility"] == wi["mean utility"]
+    assert gi["rate"] == [wi["rate"][i] for i in range(U)] and gi["load"] == [wi["load"][i] for i in range(B)]
