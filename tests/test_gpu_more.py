@@ -249,3 +249,33 @@ def test_nccl_stats_gather_matches_single_gpu():
     want = ref.metrics.cpu().numpy()
     for _, _, full in got:
         assert np.array_equal(full, want)  # sharding does not change any env's result
+
+
+def test_two_group_stepper_equals_whole_batch():
+    """mobile_env_gan_b200.pipeline.TwoGroupStepper (two halves of one handle on two streams, each a
+    dependent chain policy -> step) reproduces whole-batch stepping with the same deterministic policy."""
+    import mobile_env_gan_b200 as mbe
+    from mobile_env_gan_b200.pipeline import TwoGroupStepper
+
+    E = 4096 + 64
+    a = mbe.make("mobile-medium-central-v0", num_envs=E, autoreset=True)
+    b = mbe.make("mobile-medium-central-v0", num_envs=E, autoreset=True)
+    U, B = a.NUM_USERS, a.NUM_STATIONS
+
+    def policy(obs, group=None):  # any deterministic function of the observation
+        snr = obs.reshape(obs.shape[0], U, 2 * B + 1)[:, :, B:2 * B]
+        return (snr.argmax(dim=2) + 1 + (snr.sum(dim=2) * 7).to(torch.int32) % 2).clamp_(0, B).to(torch.int32)
+
+    a.reset(), b.reset()
+    stepper = TwoGroupStepper(a)
+    assert stepper.groups[0][1] % 32 == 0 and sum(n for _, n in stepper.groups) == E
+    steps = 27
+    stepper.run(policy, steps)
+    for _ in range(steps):
+        b.step(policy(b._obs_view()))
+    torch.cuda.synchronize()
+    for name in ("pos", "wp", "t", "episode", "conn", "rate", "utility_scaled", "obs", "reward", "done", "metrics"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    fork = __import__("mobile_env_gan_b200.scenarios.custom", fromlist=["MComCustom"]).MComCustom(config={"num_envs": 64})
+    with pytest.raises(ValueError):
+        TwoGroupStepper(fork)
