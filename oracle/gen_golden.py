@@ -99,30 +99,36 @@ CASES["two_classes"] = ([(50, 50), (150, 50), (50, 150), (150, 150), (100, 100)]
                         ep_cfg(25, {"ue": {"velocity": 8}}), 25)
 
 
+def record_case(bs_xy, nue, cfg, steps, over=None):
+    """One episode of the unmodified reference on a fixed layout -> the record the golden files hold
+    (also used live by tests/test_oracle_golden.py when /root/reference is present)."""
+    env = rh.make_fixed_layout_env(bs_xy, nue, config=cfg, bs_over=over)
+    rec = rh.record_fork_episode(env, steps)
+    if over:  # oracle-side names (Params fields)
+        ren = {"tx": "tx", "bw": "bw", "freq": "freq", "height": "bs_height"}
+        rec["bs_over"] = [{ren[k]: v for k, v in over.get(i, {}).items()} for i in range(len(bs_xy))]
+    p = env.default_config()
+    from mobile_env.core.util import deep_dict_merge
+
+    p = deep_dict_merge(p, cfg)
+    rec["params"] = {
+        "width": p["width"], "height": p["height"],
+        "ep_time": min(p["EP_MAX_TIME"], p["arrival_params"]["ep_time"]),
+        "bw": p["bs"]["bw"], "freq": p["bs"]["freq"], "tx": p["bs"]["tx"], "bs_height": p["bs"]["height"],
+        "velocity": p["ue"]["velocity"], "snr_tr": p["ue"]["snr_tr"], "noise": p["ue"]["noise"],
+        "ue_height": p["ue"]["height"],
+        "util_lower": p["utility_params"]["lower"], "util_upper": p["utility_params"]["upper"],
+        "util_coeffs": list(p["utility_params"]["coeffs"]),
+    }
+    return rec
+
+
 def main():
     # NOTE: re-running changes `mean_datarate` of existing files in the last ulp (the reference sums a
     # dict whose iteration order depends on object hashes); tests compare that field with a tolerance.
     os.makedirs(OUT, exist_ok=True)
     for name, (bs_xy, nue, cfg, steps) in CASES.items():
-        over = BS_OVERRIDES.get(name)
-        env = rh.make_fixed_layout_env(bs_xy, nue, config=cfg, bs_over=over)
-        rec = rh.record_fork_episode(env, steps)
-        if over:  # oracle-side names (Params fields)
-            ren = {"tx": "tx", "bw": "bw", "freq": "freq", "height": "bs_height"}
-            rec["bs_over"] = [{ren[k]: v for k, v in over.get(i, {}).items()} for i in range(len(bs_xy))]
-        p = env.default_config()
-        from mobile_env.core.util import deep_dict_merge
-
-        p = deep_dict_merge(p, cfg)
-        rec["params"] = {
-            "width": p["width"], "height": p["height"],
-            "ep_time": min(p["EP_MAX_TIME"], p["arrival_params"]["ep_time"]),
-            "bw": p["bs"]["bw"], "freq": p["bs"]["freq"], "tx": p["bs"]["tx"], "bs_height": p["bs"]["height"],
-            "velocity": p["ue"]["velocity"], "snr_tr": p["ue"]["snr_tr"], "noise": p["ue"]["noise"],
-            "ue_height": p["ue"]["height"],
-            "util_lower": p["utility_params"]["lower"], "util_upper": p["utility_params"]["upper"],
-            "util_coeffs": list(p["utility_params"]["coeffs"]),
-        }
+        rec = record_case(bs_xy, nue, cfg, steps, BS_OVERRIDES.get(name))
         if name == "kat1":
             s0 = rec["steps"][0]
             assert [tuple(q) for q in s0["pos"]] == KAT1_POS, s0["pos"]

@@ -52,6 +52,52 @@ def test_scalar_oracle_matches_reference(name):
         assert o["mean_datarate"] == pytest.approx(g["mean_datarate"], rel=1e-12)
 
 
+def check_scalar_against(rec, tag):
+    for k, (o, g) in enumerate(zip(run_scalar(rec), rec["steps"])):
+        assert [list(q) for q in o["pos"]] == [list(q) for q in g["pos"]], (tag, k)
+        assert o["assoc"] == g["conn"], (tag, k)
+        assert o["done"] == g["done"]
+        assert o["n_connected"] == g["n_connected"] and o["n_connections"] == g["n_connections"]
+        np.testing.assert_allclose(o["rate"], g["rate"], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(o["utility"], g["utility"], rtol=1e-12, atol=1e-15)
+        assert o["mean_utility"] == pytest.approx(g["mean_utility"], rel=1e-12, abs=1e-15)
+        assert o["mean_datarate"] == pytest.approx(g["mean_datarate"], rel=1e-12)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_scalar_oracle_matches_live_reference_on_random_scenarios(seed):
+    """Beyond the committed fixtures: the unmodified reference is run HERE on a random scenario (layout,
+    UE count, speed, radio, map, utility curve, per-BS overrides) and the oracle must replay it.  Only
+    where /root/reference exists (the build container); the fixtures carry parity elsewhere."""
+    from oracle import ref_harness
+
+    if not ref_harness.reference_available():
+        pytest.skip("the reference is only importable in the build container")
+    import json
+
+    from oracle import gen_golden
+
+    rng = np.random.default_rng(1000 + seed)
+    W, H = int(rng.integers(60, 400)), int(rng.integers(60, 400))
+    nbs, nue, steps = int(rng.integers(1, 11)), int(rng.integers(1, 21)), int(rng.integers(5, 40))
+    bs_xy = [(int(rng.integers(0, W)), int(rng.integers(0, H))) for _ in range(nbs)]
+    cfg = gen_golden.ep_cfg(steps, {
+        "width": W, "height": H, "movement_params": {"width": W, "height": H},
+        "bs": {"tx": float(rng.choice([20, 30, 40, 46])), "freq": float(rng.choice([900, 1800, 2500, 3500])),
+               "height": float(rng.choice([25, 50, 80])), "bw": float(rng.choice([5e6, 9e6, 20e6]))},
+        "ue": {"velocity": float(rng.choice([0.7, 1.5, 2.5, 3, 7.3, 10, 33])), "snr_tr": float(rng.choice([2e-8, 1e-7])),
+               "noise": float(rng.choice([1e-9, 4e-10])), "height": float(rng.choice([1.5, 1.6, 2.0]))},
+        "utility_params": {"lower": int(rng.choice([-20, -5])), "upper": int(rng.choice([20, 30])),
+                           "coeffs": tuple(int(v) for v in rng.choice([[10, 0, 10], [3, 1, 2], [5, 2, 4]]))},
+    })
+    over = None
+    if nbs >= 2 and seed % 3 == 0:
+        over = {int(rng.integers(0, nbs)): {"tx": 25.0}, int(rng.integers(0, nbs)): {"bw": 15e6, "freq": 2000.0}}
+    rec = gen_golden.record_case(bs_xy, nue, cfg, steps, over)
+    rec = json.loads(json.dumps(rec))  # the same types a fixture file gives
+    check_scalar_against(rec, f"seed {seed}: {nbs} BS, {nue} UE, {W}x{H}")
+
+
 @pytest.mark.parametrize("name", golden_names())
 def test_batch_oracle_matches_reference(name):
     rec = load_golden(name)
