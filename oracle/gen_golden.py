@@ -99,6 +99,40 @@ CASES["two_classes"] = ([(50, 50), (150, 50), (50, 150), (150, 150), (100, 100)]
                         ep_cfg(25, {"ue": {"velocity": 8}}), 25)
 
 
+def random_case(seed):
+    """A random scenario (layout, UE count, speed, radio, map, utility curve, sometimes per-BS
+    overrides): the generator behind the `rand_*` fixtures and the live cross-check in
+    tests/test_oracle_golden.py."""
+    rng = np.random.default_rng(1000 + seed)
+    W, H = int(rng.integers(60, 400)), int(rng.integers(60, 400))
+    nbs, nue, steps = int(rng.integers(1, 11)), int(rng.integers(1, 21)), int(rng.integers(5, 40))
+    bs_xy = [(int(rng.integers(0, W)), int(rng.integers(0, H))) for _ in range(nbs)]
+    cfg = ep_cfg(steps, {
+        "width": W, "height": H, "movement_params": {"width": W, "height": H},
+        "bs": {"tx": float(rng.choice([20, 30, 40, 46])), "freq": float(rng.choice([900, 1800, 2500, 3500])),
+               "height": float(rng.choice([25, 50, 80])), "bw": float(rng.choice([5e6, 9e6, 20e6]))},
+        "ue": {"velocity": float(rng.choice([0.7, 1.5, 2.5, 3, 7.3, 10, 33])), "snr_tr": float(rng.choice([2e-8, 1e-7])),
+               "noise": float(rng.choice([1e-9, 4e-10])), "height": float(rng.choice([1.5, 1.6, 2.0]))},
+        "utility_params": {"lower": int(rng.choice([-20, -5])), "upper": int(rng.choice([20, 30])),
+                           "coeffs": tuple(int(v) for v in rng.choice([[10, 0, 10], [3, 1, 2], [5, 2, 4]]))},
+    })
+    over = None
+    if nbs >= 2 and seed % 3 == 0:
+        over = {int(rng.integers(0, nbs)): {"tx": 25.0}, int(rng.integers(0, nbs)): {"bw": 15e6, "freq": 2000.0}}
+    return bs_xy, nue, cfg, steps, over
+
+
+def random_golden(seeds=range(6)):
+    """Commits a few of the random scenarios as fixtures so the GPU box (no reference) replays them."""
+    for seed in seeds:
+        bs_xy, nue, cfg, steps, over = random_case(seed)
+        rec = record_case(bs_xy, nue, cfg, steps, over)
+        path = os.path.join(OUT, f"fork_rand_{seed:02d}.json")
+        with open(path, "w") as f:
+            json.dump(rec, f, separators=(",", ":"))
+        print(os.path.basename(path), len(bs_xy), "BS", nue, "UE", steps, "steps", os.path.getsize(path), "bytes")
+
+
 def record_case(bs_xy, nue, cfg, steps, over=None):
     """One episode of the unmodified reference on a fixed layout -> the record the golden files hold
     (also used live by tests/test_oracle_golden.py when /root/reference is present)."""
@@ -279,3 +313,4 @@ if __name__ == "__main__":
     dump_golden("kat1")
     custom_epochs_golden()
     isoline_golden()
+    random_golden()

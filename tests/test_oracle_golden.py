@@ -77,22 +77,8 @@ def test_scalar_oracle_matches_live_reference_on_random_scenarios(seed):
 
     from oracle import gen_golden
 
-    rng = np.random.default_rng(1000 + seed)
-    W, H = int(rng.integers(60, 400)), int(rng.integers(60, 400))
-    nbs, nue, steps = int(rng.integers(1, 11)), int(rng.integers(1, 21)), int(rng.integers(5, 40))
-    bs_xy = [(int(rng.integers(0, W)), int(rng.integers(0, H))) for _ in range(nbs)]
-    cfg = gen_golden.ep_cfg(steps, {
-        "width": W, "height": H, "movement_params": {"width": W, "height": H},
-        "bs": {"tx": float(rng.choice([20, 30, 40, 46])), "freq": float(rng.choice([900, 1800, 2500, 3500])),
-               "height": float(rng.choice([25, 50, 80])), "bw": float(rng.choice([5e6, 9e6, 20e6]))},
-        "ue": {"velocity": float(rng.choice([0.7, 1.5, 2.5, 3, 7.3, 10, 33])), "snr_tr": float(rng.choice([2e-8, 1e-7])),
-               "noise": float(rng.choice([1e-9, 4e-10])), "height": float(rng.choice([1.5, 1.6, 2.0]))},
-        "utility_params": {"lower": int(rng.choice([-20, -5])), "upper": int(rng.choice([20, 30])),
-                           "coeffs": tuple(int(v) for v in rng.choice([[10, 0, 10], [3, 1, 2], [5, 2, 4]]))},
-    })
-    over = None
-    if nbs >= 2 and seed % 3 == 0:
-        over = {int(rng.integers(0, nbs)): {"tx": 25.0}, int(rng.integers(0, nbs)): {"bw": 15e6, "freq": 2000.0}}
+    bs_xy, nue, cfg, steps, over = gen_golden.random_case(seed)
+    W, H, nbs = cfg["width"], cfg["height"], len(bs_xy)
     rec = gen_golden.record_case(bs_xy, nue, cfg, steps, over)
     rec = json.loads(json.dumps(rec))  # the same types a fixture file gives
     check_scalar_against(rec, f"seed {seed}: {nbs} BS, {nue} UE, {W}x{H}")
