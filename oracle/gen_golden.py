@@ -133,6 +133,40 @@ def random_golden(seeds=range(6)):
         print(os.path.basename(path), len(bs_xy), "BS", nue, "UE", steps, "steps", os.path.getsize(path), "bytes")
 
 
+GYM_PIECES = {
+    # name: (bs_xy, num_ues, config, steps, per-BS overrides, action seed)
+    "medium": ([(50, 50), (150, 50), (50, 150), (150, 150)], 15, ep_cfg(20), 20, None, 11),
+    "small_fast": ([(110, 130), (65, 80), (120, 30)], 5, ep_cfg(30, {"ue": {"velocity": 9}}), 30, None, 12),
+    "custom_10bs": ([(40, 150), (100, 100), (160, 40), (30, 30), (170, 170), (100, 20), (20, 100), (150, 110),
+                     (90, 180), (60, 60)], 7, ep_cfg(20, {"ue": {"velocity": 10}}), 20, None, 13),
+    "two_classes": ([(50, 50), (150, 50), (50, 150), (150, 150), (100, 100)], 12,
+                    ep_cfg(25, {"ue": {"velocity": 8}}), 25, {1: {"tx": 30}, 3: {"tx": 30, "bw": 18e6}}, 14),
+}
+
+
+def gym_pieces_golden():
+    """GYM-ORDER episodes executed by the reference's own primitives (ref_harness.
+    record_gym_pieces_episode): pins update_connections, the multi-connection allocation / per-UE
+    sum, utilities and allStationUtilities of the GYM step; the stage order and the action semantics
+    stay this build's specification.  -> tests/golden/gymref_*.json"""
+    for name, (bs_xy, nue, cfg, steps, over, aseed) in GYM_PIECES.items():
+        rng = np.random.default_rng(aseed)
+        # mostly connect requests early on, then a mix with NOOPs and disconnects
+        actions = [[int(a) for a in rng.integers(0, len(bs_xy) + 1, size=nue)] for _ in range(steps)]
+        env = rh.make_fixed_layout_env(bs_xy, nue, config=cfg, bs_over=over)
+        rec = rh.record_gym_pieces_episode(env, actions)
+        shell = record_case(bs_xy, nue, cfg, 1, over)  # params / bs_over in the fixtures' format
+        rec["params"] = shell["params"]
+        if over:
+            rec["bs_over"] = shell["bs_over"]
+        multi = sum(len(c) > 1 for st in rec["steps"] for c in st["conn"])
+        assert multi > 0, "the fixture must exercise UEs connected to several BSs"
+        path = os.path.join(OUT, f"gymref_{name}.json")
+        with open(path, "w") as f:
+            json.dump(rec, f, separators=(",", ":"))
+        print(os.path.basename(path), steps, "steps,", multi, "multi-connection UE-steps,", os.path.getsize(path), "bytes")
+
+
 def record_case(bs_xy, nue, cfg, steps, over=None):
     """One episode of the unmodified reference on a fixed layout -> the record the golden files hold
     (also used live by tests/test_oracle_golden.py when /root/reference is present)."""
@@ -314,3 +348,4 @@ if __name__ == "__main__":
     custom_epochs_golden()
     isoline_golden()
     random_golden()
+    gym_pieces_golden()

@@ -17,7 +17,12 @@ PARITY STATUS
     from the pieces that do survive in the fork: ``update_connections``
     (base.py:221-227), ``check_connectivity`` (212-214), ``available_connections``
     (216-218), ``allStationUtilities`` (438-447), ``NOOP_ACTION`` (29),
-    ``metrics.mean_utility`` (metrics.py:25-28).
+    ``metrics.mean_utility`` (metrics.py:25-28).  The arithmetic of those stages IS pinned:
+    ``ref_harness.record_gym_pieces_episode`` runs GYM-order episodes with the reference's own
+    primitives (incl. UEs on several BSs through ``allocateDataRate2User`` /
+    ``user_total_datarates``) and ``step_gym`` must replay ``tests/golden/gymref_*.json``; the
+    stage order, the action semantics, the observation layout and the multi-agent reward remain
+    this build's own specification.
 
 Two forms are provided:
   ``ScalarEnv``   per-entity Python loops, op-for-op like the reference (slow; also the
@@ -386,6 +391,7 @@ class ScalarEnv:
             "n_connected": sum(1 for c in self.conn if c),
             "mean_utility": float(np.mean(util)),
             "mean_datarate": float(np.mean(list(total.values()))) if total else 0.0,
+            "bs_utility": [float(v) for v in self._bs_utilities(bs_conns)],  # base.py:438-447
         }
         # (6) move, clock, departures
         self._move_all()

@@ -201,3 +201,90 @@ def record_fork_episode(env, steps, init_pos=None):
         )
     mv.move = orig_move
     return rec
+
+
+def record_gym_pieces_episode(env, actions, init_pos=None):
+    """GYM-order episode assembled from the reference's OWN primitives.
+
+    The fork has no GYM step, so the ORDER below (update_connections -> action toggle -> allocate ->
+    utility -> BS utilities -> move -> clock) is this build's specification; but every stage is
+    executed by the unmodified reference code on its own objects:
+
+      * ``MComCore.update_connections``            base.py:221-227
+      * ``MComCore.check_connectivity``            base.py:212-214   (gate of a connect action)
+      * ``MComCore.allocateDataRate2User``         base.py:421-435   (scheduler share + round)
+      * ``MComCore.user_total_datarates``          base.py:413-418   (a UE on SEVERAL BSs: the
+                                                   multi-connection sum the FORK step never exercises)
+      * ``utilityModel.calculateUtility/scaleUtility``  base.py:253-258, utilities.py:44-55
+      * ``MComCore.allStationUtilities``           base.py:438-447
+      * ``movementModel.move``                     movement.py:42-62
+      * clock / leaving UEs                        base.py:280-291
+
+    ``actions``: [T][U] ints, 0 = NOOP (base.py:29), a > 0 toggles BS a-1.  Returns plain lists like
+    ``record_fork_episode`` (waypoint triples for injection included)."""
+    env.reset()
+    ues = [env.userDict[k] for k in sorted(env.userDict)]
+    bss = [env.stationDict[k] for k in sorted(env.stationDict)]
+    if init_pos is not None:
+        for ue, (x, y) in zip(ues, init_pos):
+            ue.x, ue.y = x, y
+    rec = {"bs_xy": [[bs.x, bs.y] for bs in bss], "init_pos": [[int(ue.x), int(ue.y)] for ue in ues],
+           "actions": [list(map(int, a)) for a in actions], "steps": []}
+    mv = env.movementModel
+    orig_move = mv.move
+    targets = {}
+
+    def logged_move(ue):
+        had = ue in mv.userMoveDirection
+        out = orig_move(ue)
+        wp = mv.userMoveDirection.get(ue, out)
+        targets[ue.ue_id] = (int(wp[0]), int(wp[1]), 0 if had else 1)
+        return out
+
+    mv.move = logged_move
+    for acts in actions:
+        targets.clear()
+        env.update_connections()
+        for ue, a in zip(ues, acts):
+            if a == 0 or ue not in env.activeUsers:
+                continue
+            bs = bss[a - 1]
+            if ue in env.bs2ue_connections[bs]:
+                env.bs2ue_connections[bs].remove(ue)
+            elif env.check_connectivity(bs, ue):
+                env.bs2ue_connections[bs].add(ue)
+        env.bs2ue_dataRates = {}
+        for bs in bss:
+            env.bs2ue_dataRates.update(env.allocateDataRate2User(bs))
+        env.allUserDataRates = env.user_total_datarates(env.bs2ue_dataRates)
+        env.ue_utilities = {
+            ue: env.utilityModel.scaleUtility(env.utilityModel.calculateUtility(env.allUserDataRates.get(ue, 0.0)))
+            for ue in env.activeUsers
+        }
+        bs_util = env.allStationUtilities()
+        conn = [sorted(bs.bs_id for bs in bss if ue in env.bs2ue_connections[bs]) for ue in ues]
+        step = {
+            "conn": conn,
+            "pair_rates": sorted([ue.ue_id, bs.bs_id, float(r)] for (bs, ue), r in env.bs2ue_dataRates.items()),
+            "rate": [float(env.allUserDataRates.get(ue, 0.0)) for ue in ues],
+            "utility": [float(env.ue_utilities.get(ue, float("nan"))) for ue in ues],
+            "bs_utility": [float(bs_util[bs]) for bs in bss],
+            "connectable": [[bool(env.check_connectivity(bs, ue)) for bs in bss] for ue in ues],
+        }
+        for ue in env.activeUsers:
+            ue.x, ue.y = mv.move(ue)
+        env.time += 1
+        leaving = set(ue for ue in env.activeUsers if ue.exitTime <= env.time)
+        for bs, cues in env.bs2ue_connections.items():
+            env.bs2ue_connections[bs] = cues - leaving
+        env.activeUsers = sorted(
+            [ue for ue in env.userDict.values() if ue.exitTime > env.time >= ue.startTime], key=lambda ue: ue.ue_id)
+        step.update({
+            "pos": [[int(ue.x), int(ue.y)] for ue in ues],
+            "wp": [list(targets.get(ue.ue_id, (-1, -1, 0))) for ue in ues],
+            "conn_after": [sorted(bs.bs_id for bs in bss if ue in env.bs2ue_connections[bs]) for ue in ues],
+            "done": bool(env.time_is_up),
+        })
+        rec["steps"].append(step)
+    mv.move = orig_move
+    return rec

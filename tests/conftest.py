@@ -32,6 +32,17 @@ def load_golden(name):
         return json.load(f)
 
 
+def gymref_names():
+    return sorted(f[len("gymref_"):-len(".json")] for f in os.listdir(GOLDEN_DIR) if f.startswith("gymref_"))
+
+
+def load_gymref(name):
+    """GYM-order episodes executed by the reference's own primitives (oracle/ref_harness.py:
+    record_gym_pieces_episode, fixtures written by oracle/gen_golden.py:gym_pieces_golden)."""
+    with open(os.path.join(GOLDEN_DIR, f"gymref_{name}.json")) as f:
+        return json.load(f)
+
+
 def golden_waypoints(rec):
     """Per-UE list of waypoints in draw order, from the recorded (wx, wy, drew) triples."""
     nue = len(rec["init_pos"])

@@ -9,7 +9,7 @@ oracle.  Bars (BASELINE.json north_star):
 import numpy as np
 import pytest
 
-from conftest import golden_names, golden_waypoints, load_golden
+from conftest import gymref_names, load_gymref, golden_names, golden_waypoints, load_golden
 from mirror import Mirror, conn_bits, conn_bool_from_words
 
 pytestmark = pytest.mark.gpu
@@ -274,6 +274,69 @@ def test_gym_matches_oracle(scen, handler, autoreset):
         m = env.metrics.cpu().numpy()
         assert np.array_equal(m[:, 0], out["n_connections"]) and np.array_equal(m[:, 1], out["n_connected"])
         close(m[:, 3], out["mean_datarate"])
+
+
+@pytest.mark.parametrize("handler", ["central", "ma"])
+@pytest.mark.parametrize("name", gymref_names())
+def test_gym_step_replays_reference_primitive_episodes(name, handler):
+    """GYM-order episodes executed by the reference's OWN update_connections / allocateDataRate2User /
+    user_total_datarates / utilities / allStationUtilities / move (tests/golden/gymref_*.json,
+    oracle/ref_harness.py:record_gym_pieces_episode) replayed through the CUDA GYM step with the
+    recorded actions and injected waypoints: connection sets (UEs on several BSs included),
+    positions, done and FP64 rates bit-exact; utilities, reward and the broadcast BS utilities 1e-5."""
+    rec = load_gymref(name)
+    E, U, B = 5, len(rec["init_pos"]), len(rec["bs_xy"])
+    extra = {"num_envs": E, "mode": "gym", "handler": handler}
+    if rec.get("bs_over"):
+        MComCore, BaseStation, UserEquipment = _mods()
+        from mobile_env_gan_b200.core.util import deep_dict_merge
+
+        config = golden_config(rec, extra)
+        cfg = deep_dict_merge(MComCore.default_config(), config)
+        ren = {"tx": "tx", "bw": "bw", "freq": "freq", "bs_height": "height"}
+        stations = []
+        for i, xy in enumerate(rec["bs_xy"]):
+            kw = dict(cfg["bs"])
+            kw.update({ren[k]: v for k, v in rec["bs_over"][i].items()})
+            stations.append(BaseStation(i, tuple(xy), **kw))
+        env = MComCore(stations, [UserEquipment(i, **cfg["ue"]) for i in range(U)], config)
+    else:
+        env = make_env(rec["bs_xy"], U, golden_config(rec, extra))
+    seq = golden_waypoints(rec)
+    K = max(1, max(len(s) for s in seq))
+    wp = np.zeros((E, U, K, 2), dtype=np.int16)
+    for u, s in enumerate(seq):
+        for k, w in enumerate(s):
+            wp[:, u, k] = w
+    env.reset()
+    env.inject_waypoints(wp)
+    env.set_positions(np.broadcast_to(np.array(rec["init_pos"]), (E, U, 2)).copy())
+    F = env.plan.feature_size
+    seen_bcast = 0
+    for k, (acts, g) in enumerate(zip(rec["actions"], rec["steps"])):
+        a = torch.tensor(acts, dtype=torch.int32, device=env.device).expand(E, U).contiguous()
+        obs, rew, term, trunc, info = env.step(a)
+        want_conn = [sum(1 << b for b in c) for c in g["conn_after"]]
+        for e in (0, E - 1):
+            assert (env.conn[e].cpu().numpy().astype(np.int64) & 0xFFFFFFFF).tolist() == want_conn, (name, k)
+            assert env.pos[e].cpu().tolist() == g["pos"], (name, k)
+            assert env.rate[e].cpu().tolist() == g["rate"], (name, k)  # FP64, bit-exact, multi-BS sums included
+            close(env.utility_scaled[e].cpu(), g["utility"], f"{name} utility step {k}")
+            assert bool(trunc[e]) == g["done"]
+            m = env.metrics[e].cpu().tolist()
+            assert m[0] == sum(len(c) for c in g["conn"]) and m[1] == sum(1 for c in g["conn"] if c)
+            if handler == "central":
+                close(float(rew[e]), float(np.mean(g["utility"])), "central reward = mean utility (metrics.py:25-28)")
+            elif not g["done"]:
+                # columns 2B+1 .. 3B of a multi-agent row: allStationUtilities (base.py:438-447) of the BSs
+                # the UE can reach from its new position, -1 elsewhere
+                row = obs[e].reshape(U, F)[:, 2 * B + 1:3 * B + 1].cpu().numpy()
+                for u in range(U):
+                    for b in range(B):
+                        if row[u, b] != -1.0:
+                            close(row[u, b], g["bs_utility"][b], f"{name} bs utility step {k}")
+                            seen_bcast += 1
+    assert handler == "central" or seen_bcast > 0
 
 
 def test_gym_random_layouts_autoreset():

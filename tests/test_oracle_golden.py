@@ -8,7 +8,7 @@ to 1e-12 relative (same arithmetic, possibly different libm entry points)."""
 import numpy as np
 import pytest
 
-from conftest import golden_names, golden_waypoints, load_golden
+from conftest import gymref_names, load_gymref, golden_names, golden_waypoints, load_golden
 from oracle import mbe_oracle as orc
 
 
@@ -62,6 +62,36 @@ def check_scalar_against(rec, tag):
         np.testing.assert_allclose(o["utility"], g["utility"], rtol=1e-12, atol=1e-15)
         assert o["mean_utility"] == pytest.approx(g["mean_utility"], rel=1e-12, abs=1e-15)
         assert o["mean_datarate"] == pytest.approx(g["mean_datarate"], rel=1e-12)
+
+
+@pytest.mark.parametrize("name", gymref_names())
+@pytest.mark.parametrize("handler", ["central", "ma"])
+def test_scalar_oracle_gym_step_matches_reference_primitives(name, handler):
+    """The GYM step of the oracle against GYM-order episodes executed by the reference's own
+    update_connections / allocateDataRate2User / user_total_datarates / utility / allStationUtilities /
+    move (fixtures from oracle/gen_golden.py:gym_pieces_golden): connection sets incl. UEs on several
+    BSs, per-link and per-UE rates, utilities, BS utilities, positions, done."""
+    rec = load_gymref(name)
+    p = params_of(rec)
+    seq = golden_waypoints(rec)
+    env = orc.ScalarEnv(p, rec["bs_xy"], len(rec["init_pos"]), wp_source=lambda u, k: seq[u][k],
+                        bs_over=rec.get("bs_over"))
+    env.reset(rec["init_pos"])
+    for k, (acts, g) in enumerate(zip(rec["actions"], rec["steps"])):
+        ok = [[env.connectable(b, u) for b in range(len(rec["bs_xy"]))] for u in range(env.num_ues)]
+        assert ok == g["connectable"], (name, k)
+        obs, rew, done, info = env.step_gym(acts, handler)
+        assert info["conn"] == g["conn"], (name, k)
+        got = sorted([u, b, float(r)] for (b, u), r in info["pair_rates"].items())
+        assert [q[:2] for q in got] == [q[:2] for q in g["pair_rates"]], (name, k)
+        np.testing.assert_allclose([q[2] for q in got], [q[2] for q in g["pair_rates"]], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(info["rate"], g["rate"], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(info["utility"], g["utility"], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(info["bs_utility"], g["bs_utility"], rtol=1e-12, atol=1e-15)
+        assert [list(q) for q in info["pos"]] == g["pos"], (name, k)
+        assert done == g["done"]
+        if handler == "central":
+            assert rew == pytest.approx(float(np.mean(g["utility"])), rel=1e-12, abs=1e-15)  # metrics.py:25-28
 
 
 @pytest.mark.parametrize("seed", range(12))
