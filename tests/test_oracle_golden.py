@@ -227,3 +227,24 @@ def test_custom_epochs_oracle_matches_reference():
             assert [list(q) for q in o["pos"]] == g["pos"] and o["assoc"] == g["conn"], k
             assert o["rate"] == g["rate"] and o["done"] == g["done"]
             np.testing.assert_allclose(o["utility"], g["utility"], rtol=1e-12, atol=1e-15)
+
+
+def test_repaired_rate_fair_matches_the_reference_scalar():
+    """RateFair.share in the reference returns the scalar 1/sum(1/r) (schedules.py:26-29) and therefore
+    cannot run inside allocateDataRate2User; the repaired scheduler gives every UE of the BS exactly
+    that value (order-independent 2^-50 fixed-point sum).  Checked against the reference's scalar."""
+    from oracle import ref_harness
+
+    if not ref_harness.reference_available():
+        pytest.skip("the reference is only importable in the build container")
+    ref_harness.import_reference()
+    from mobile_env.core.schedules import RateFair, ResourceFair
+
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        n = int(rng.integers(1, 40))
+        rates = (10.0 ** rng.uniform(-1, 6.6, size=n)).tolist()
+        want = RateFair().share(None, rates)
+        assert orc.rate_fair_share(rates) == pytest.approx(want, rel=1e-8)
+        assert orc.rate_fair_share(rates[::-1]) == orc.rate_fair_share(rates)  # order independent
+        assert [r / n for r in rates] == ResourceFair().share(None, rates)
