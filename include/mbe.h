@@ -56,7 +56,12 @@ enum { MBE_SCHED_RESOURCE_FAIR = 0, MBE_SCHED_PROPORTIONAL_FAIR = 1, MBE_SCHED_R
 enum { MBE_BS_SHARED = 0, MBE_BS_PER_ENV = 1 };
 enum { MBE_MAX_CLASSES = 8 };
 /* mbe_config.flags */
-enum { MBE_FLAG_GENERIC_KERNEL = 1 }; /* never use the shape-specialised fused kernels */
+enum {
+  MBE_FLAG_GENERIC_KERNEL = 1,    /* never use the shape-specialised fused kernels */
+  MBE_FLAG_SHARED_TRAJECTORY = 2, /* all envs draw the SAME UE initial positions and waypoints (the fork: movement
+                                     reset_rng_episode=True makes every epoch replay one UE trajectory, base.py:130-134;
+                                     with env index = epoch number only the BS layouts differ) */
+};
 
 /* phases of one step (bit mask for mbe_stage); the fused step runs all of them in one launch.
  * FORK order: MOVE, PRE, CLOCK.  GYM order: PRE, MOVE, CLOCK, POST. */

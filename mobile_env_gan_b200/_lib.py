@@ -17,6 +17,7 @@ SCHED_RESOURCE_FAIR, SCHED_PROPORTIONAL_FAIR, SCHED_RATE_FAIR = 0, 1, 2
 BS_SHARED, BS_PER_ENV = 0, 1
 MAX_CLASSES = 8
 FLAG_GENERIC_KERNEL = 1
+FLAG_SHARED_TRAJECTORY = 2
 PHASE_MOVE, PHASE_PRE, PHASE_CLOCK, PHASE_POST, PHASE_ALL = 1, 2, 4, 8, 15
 
 

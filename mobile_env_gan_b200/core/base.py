@@ -59,6 +59,7 @@ class Plan:
     move_d2max: int
     utility: tuple
     scheduler: int = 0
+    shared_trajectory: bool = False
     classes: List[dict] = field(default_factory=list)
     bs_class: Optional[np.ndarray] = None
     bs_xy: Optional[np.ndarray] = None  # shared layout [B,2] int16
@@ -108,6 +109,10 @@ class MComCore:
             "bs_random": None,  # (min, max): draw a BS layout per env and episode (custom.py:68-77)
             "max_bs": None,  # BS slots when bs_random is used
             "generic_kernel": False,  # True: never use the shape-specialised fused kernels
+            # True: every env draws the same UE initial positions / waypoints (only BS layouts differ);
+            # "follow_movement": True iff movement_params.reset_rng_episode -- the fork, where that flag
+            # makes every epoch replay one UE trajectory (base.py:130-134) and env index = epoch number
+            "shared_trajectory": False,
         }
 
     @classmethod
@@ -173,6 +178,9 @@ class MComCore:
         mv = movement.device_params(ue0.velocity)
         w1, w2, w3 = utility.coeffs
         ep_time = int(min(config["EP_MAX_TIME"], arrival.ep_time))  # base.py:407-409 with NoDeparture
+        shared = config.get("shared_trajectory", False)
+        if shared == "follow_movement":
+            shared = bool(movement.reset_rng_episode)
         return Plan(
             num_envs=int(config["num_envs"]), num_ues=len(users), num_bs=nbs, mode=mode, handler=handler,
             bs_layout=layout, bs_random=bs_random, autoreset=bool(config.get("autoreset")),
@@ -180,7 +188,8 @@ class MComCore:
             env_offset=int(config.get("env_offset", 0)), seed=int(movement.seed),
             width=width, height=height, velocity=mv["velocity"], move_d2max=mv["move_d2max"],
             utility=(float(utility.lower), float(utility.upper), float(w1), float(w2), float(w3)),
-            scheduler=int(scheduler.kernel_id), classes=classes, bs_class=bs_class, bs_xy=bs_xy,
+            scheduler=int(scheduler.kernel_id), shared_trajectory=bool(shared), classes=classes, bs_class=bs_class,
+            bs_xy=bs_xy,
         )
 
     @staticmethod
@@ -279,7 +288,8 @@ class MComCore:
         cfg.width, cfg.height, cfg.velocity = p.width, p.height, p.velocity
         cfg.util_lower, cfg.util_upper, cfg.util_w1, cfg.util_w2, cfg.util_w3 = p.utility
         cfg.num_classes = len(p.classes)
-        cfg.flags = _lib.FLAG_GENERIC_KERNEL if self.config.get("generic_kernel") else 0
+        cfg.flags = (_lib.FLAG_GENERIC_KERNEL if self.config.get("generic_kernel") else 0) | (
+            _lib.FLAG_SHARED_TRAJECTORY if p.shared_trajectory else 0)
         for i, c in enumerate(p.classes):
             lut = np.ascontiguousarray(c["rate_lut"], dtype=np.float64)
             self._keepalive.append(lut)

@@ -189,6 +189,7 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   a.epw = env->big ? 1 : 32 / a.U;
   a.epb = a.epw * mbe::kWarpsPerBlock;
   a.env_offset = (unsigned)cfg->env_offset;
+  a.traj_gid_mask = (cfg->flags & MBE_FLAG_SHARED_TRAJECTORY) ? 0u : 0xffffffffu;
   a.ep_time = cfg->ep_time;
   a.autoreset = cfg->autoreset;
   a.reset_rng_episode = cfg->reset_rng_episode;

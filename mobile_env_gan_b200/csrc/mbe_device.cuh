@@ -48,6 +48,7 @@ struct StepArgs {
   int epb;  // envs per block
   int op, phases;
   unsigned env_offset;
+  unsigned traj_gid_mask;  // 0xffffffff, or 0 when all envs share the UE trajectories
   // scenario
   int ep_time, autoreset, reset_rng_episode, bs_per_env, bs_rand_min, bs_rand_max;
   unsigned seed_lo, seed_hi;
@@ -151,6 +152,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 // int(rng.uniform(0, W)) (movement.py:45-46, 69-70).  Counter = (env gid, ue, t, purpose+4*salt).
 __device__ __forceinline__ void philox_point(const StepArgs& a, unsigned gid, unsigned ue, unsigned t,
                                           unsigned purpose, unsigned salt, int& x, int& y) {
+  // UE trajectories (waypoints, initial positions) can be shared by all envs -- the fork's dataset:
+  // movement reset_rng_episode=True gives every epoch the same UE trajectory (base.py:130-134) and
+  // only the BS layout differs; layouts always use the env's own id
+  if (purpose != P_BSLAYOUT) gid &= a.traj_gid_mask;
   uint4 r = philox4x32_10(make_uint4(gid, ue, t, purpose + 4u * salt), make_uint2(a.seed_lo, a.seed_hi));
   if (a.wh_int) {  // integer map size: floor(r * 2^-32 * W) is exactly the high word of r * W
     x = (int)__umulhi(r.x, (unsigned)a.wh_int_w);

@@ -1,7 +1,10 @@
 """MComCustom, batched (reference mobile_env/scenarios/custom.py:12-85): 7 UEs at velocity 10
 and, per env and per episode, 5..10 base stations at uniform integer positions.  The reference
 draws the layout from the unseeded global ``random`` (custom.py:68-77); here it is Philox keyed
-by (seed, env, episode), so runs are reproducible."""
+by (seed, env, episode), so runs are reproducible.  UE trajectories follow the fork: with the default
+``movement_params.reset_rng_episode=True`` every epoch of the reference replays ONE UE trajectory
+(base.py:130-134), so with env index = epoch number all envs share it (``shared_trajectory``) and only
+the BS layouts differ -- which is what makes the layout scores comparable."""
 from __future__ import annotations
 
 from ..core.base import MComCore
@@ -16,7 +19,8 @@ class MComCustom(MComCore):
     def default_config(cls):
         config = super().default_config()
         config["ue"].update({"velocity": 10})
-        config.update({"bs_random": cls.BS_RANGE, "max_bs": cls.BS_RANGE[1], "mode": "fork"})
+        config.update({"bs_random": cls.BS_RANGE, "max_bs": cls.BS_RANGE[1], "mode": "fork",
+                       "shared_trajectory": "follow_movement"})
         return config
 
     def __init__(self, config=None, render_mode=None):

@@ -31,6 +31,8 @@ class Mirror:
         self.rre = pl.reset_rng_episode
         self.bs_random = pl.bs_random if pl.bs_random[1] > 0 else None
         self.gid = self.off + np.arange(self.E)
+        # UE trajectories shared by all envs (MBE_FLAG_SHARED_TRAJECTORY): env id 0 in their counters
+        self.traj_gid = np.zeros_like(self.gid) if getattr(pl, "shared_trajectory", False) else self.gid
         self.ue = np.arange(self.U)
         self.episode = np.full(self.E, -1, dtype=np.int64)
         self.t = np.zeros(self.E, dtype=np.int64)
@@ -51,7 +53,7 @@ class Mirror:
         sel = np.asarray(sel, dtype=bool)
         self.episode = np.where(sel, self.episode + 1, self.episode)
         self.t = np.where(sel, 0, self.t)
-        x, y = orc.philox_point(self.seed, self.gid[:, None], self.ue[None, :], 0, orc.PURPOSE_INITPOS,
+        x, y = orc.philox_point(self.seed, self.traj_gid[:, None], self.ue[None, :], 0, orc.PURPOSE_INITPOS,
                                 self._salt()[:, None], self.p.width, self.p.height)
         init = np.stack([x, y], axis=-1)
         self.pos = np.where(sel[:, None, None], init, self.pos)
@@ -96,7 +98,7 @@ class Mirror:
         return obs
 
     def new_wp(self):
-        x, y = orc.philox_point(self.seed, self.gid[:, None], self.ue[None, :], self.t[:, None],
+        x, y = orc.philox_point(self.seed, self.traj_gid[:, None], self.ue[None, :], self.t[:, None],
                                 orc.PURPOSE_WAYPOINT, self._salt()[:, None], self.p.width, self.p.height)
         return np.stack([x, y], axis=-1)
 

@@ -279,3 +279,39 @@ def test_two_group_stepper_equals_whole_batch():
     fork = __import__("mobile_env_gan_b200.scenarios.custom", fromlist=["MComCustom"]).MComCustom(config={"num_envs": 64})
     with pytest.raises(ValueError):
         TwoGroupStepper(fork)
+
+
+def test_custom_scenario_shares_the_ue_trajectory_like_the_fork():
+    """In the fork every epoch replays ONE UE trajectory (movement reset_rng_episode=True,
+    base.py:130-134) over a fresh BS layout; with env index = epoch number all envs of MComCustom
+    therefore share positions and waypoints while their layouts differ -- across episodes too."""
+    from mobile_env_gan_b200.scenarios.custom import MComCustom
+
+    E = 96
+    env = MComCustom(config={"num_envs": E, "autoreset": True, "env_offset": 7})
+    assert env.plan.shared_trajectory
+    mir = Mirror(env)
+    env.reset(), mir.reset()
+    first_episode = []
+    for k in range(45):
+        env.step(0, k)
+        out = mir.step_fork()
+        pos = env.pos.cpu().numpy()
+        assert np.array_equal(pos, out["pos_after"]), k
+        assert (pos == pos[:1]).all(), k  # one trajectory for every env
+        assert np.array_equal(env.bs_xy.cpu().numpy(), mir.bs) and np.array_equal(env.nbs.cpu().numpy(), mir.nbs)
+        if k < 20:
+            first_episode.append(pos[0].copy())
+        elif k < 40:
+            assert np.array_equal(pos[0], first_episode[k - 20]), k  # and for every episode
+    bs = env.bs_xy.cpu().numpy()
+    assert len({bs[e].tobytes() for e in range(E)}) == E  # but every env has its own layout
+    own = MComCustom(config={"num_envs": E, "movement_params": {"reset_rng_episode": False}})
+    assert not own.plan.shared_trajectory
+    own.reset()
+    own.step(0, 0)
+    p = own.pos.cpu().numpy()
+    assert len({p[e].tobytes() for e in range(E)}) > E // 2
+    forced = MComCustom(config={"num_envs": E, "shared_trajectory": False})
+    forced.reset()
+    assert len({forced.pos[e].cpu().numpy().tobytes() for e in range(E)}) > E // 2
