@@ -486,6 +486,15 @@ class MComCore:
 
         return EnvView(self, e)
 
+    def bs_isolines(self, drate: float, env: int = 0) -> Dict:
+        """Coverage outline of every base station (reference base.py:450-460, a rendering helper):
+        ``{BaseStation: (xs, ys)}`` from ``Channel.isoline`` with the default UE parameters.  ``env``
+        selects the layout when layouts are per env (``MComCustom``).  Host-side, off the step path."""
+        ue_config = self.default_config()["ue"]
+        per_env = self.plan.bs_layout == _lib.BS_PER_ENV
+        stations = (self.view(env).stationDict if per_env else self.stationDict).values()
+        return {bs: self.channelModel.isoline(bs, ue_config, (self.width, self.height), drate) for bs in stations}
+
     def state_dict(self):
         keys = ("pos", "wp", "t", "episode", "bs_xy", "nbs", "conn", "assoc", "rate", "utility_scaled", "done")
         return {k: getattr(self, k).clone() for k in keys if getattr(self, k) is not None}

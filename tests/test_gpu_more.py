@@ -315,3 +315,21 @@ def test_custom_scenario_shares_the_ue_trajectory_like_the_fork():
     forced = MComCustom(config={"num_envs": E, "shared_trajectory": False})
     forced.reset()
     assert len({forced.pos[e].cpu().numpy().tobytes() for e in range(E)}) > E // 2
+
+
+def test_bs_isolines_uses_the_reference_outline():
+    """MComCore.bs_isolines (reference base.py:450-460) = Channel.isoline per BS with the default UE;
+    the first BS of the small scenario is one of the golden outlines the reference produced."""
+    import json
+
+    from conftest import GOLDEN_DIR
+
+    with open(os.path.join(GOLDEN_DIR, "isoline.json")) as f:
+        gold = json.load(f)
+    case = next(c for c in gold["cases"] if c["pos"] == [110, 130] and c["dthresh"] == 5.0 and c["num"] == 32)
+    env = make_env([(110, 130), (65, 80), (120, 30)], 5, {"num_envs": 4})
+    with np.errstate(all="ignore"):
+        lines = env.bs_isolines(5.0)
+    assert len(lines) == 3
+    xs, ys = lines[env.stationDict[0]]
+    assert list(map(float, xs)) == case["xs"] and list(map(float, ys)) == case["ys"]
