@@ -10,15 +10,15 @@
 #include "mbe_device.cuh"
 
 // Resident CTAs (128 threads) per SM the register allocation is held to, tuned per kernel on B200
-// (profiles/README.md): the small central shapes run best near full occupancy (14 CTAs, 36 registers;
-// 16 / 32 registers before the L2 prefetch), the multi-agent and wide shapes need more registers for
-// their per-BS arrays (large central 9 CTAs, large multi-agent 8).
+// (profiles/README.md): the small central shapes run at full occupancy with 32 registers (10..16 CTAs
+// measure the same within noise), the multi-agent and wide shapes need more registers for their
+// per-BS arrays (large central 9 CTAs = 56 registers, large multi-agent 8 = 64).
 #ifndef MBE_SPEC_MIN_BLOCKS
 #define MBE_SPEC_MIN_BLOCKS(MODE, HANDLER, B) \
   ((B) <= 4 ? ((HANDLER) == 1 ? 12 : MBE_SMALL_C_BLOCKS) : (B) <= 10 ? ((MODE) == 0 ? 11 : 10) : ((HANDLER) == 1 ? MBE_LARGE_MA_BLOCKS : MBE_LARGE_C_BLOCKS))
 #endif
 #ifndef MBE_SMALL_C_BLOCKS
-#define MBE_SMALL_C_BLOCKS 14
+#define MBE_SMALL_C_BLOCKS 16
 #endif
 #ifndef MBE_LARGE_C_BLOCKS
 #define MBE_LARGE_C_BLOCKS 9
