@@ -288,3 +288,23 @@ def test_monitor_frames_match_reference_monitor():
     gi, wi = mine.info(env), ref.info()
     assert gi["mean utility"] == wi["mean utility"]
     assert gi["rate"] == [wi["rate"][i] for i in range(U)] and gi["load"] == [wi["load"][i] for i in range(B)]
+
+
+def test_shared_trajectory_follows_the_forks_movement_flag():
+    """MComCustom mirrors the fork: movement_params.reset_rng_episode=True (the reference default,
+    base.py:130-134) makes every epoch replay one UE trajectory, so with env index = epoch number all
+    envs share the trajectory draws; the Gymnasium-shaped scenarios keep independent envs."""
+    from mobile_env_gan_b200.scenarios.custom import MComCustom
+
+    def plan_of(cls, extra, stations=()):
+        cfg = cls.seeding(deep_dict_merge(cls.default_config(), extra))
+        users = [UserEquipment(i, **cfg["ue"]) for i in range(7)]
+        return cls.build_plan(list(stations), users, cfg)
+
+    p = plan_of(MComCustom, {"num_envs": 64})
+    assert p.shared_trajectory and p.reset_rng_episode and p.bs_random == (5, 10) and p.num_bs == 10
+    assert not plan_of(MComCustom, {"num_envs": 64, "movement_params": {"reset_rng_episode": False}}).shared_trajectory
+    assert not plan_of(MComCustom, {"num_envs": 64, "shared_trajectory": False}).shared_trajectory
+    bs = [BaseStation(0, (10, 10), **MComCore.default_config()["bs"])]
+    assert not plan_of(MComCore, {"num_envs": 64}, bs).shared_trajectory
+    assert plan_of(MComCore, {"num_envs": 64, "shared_trajectory": True}, bs).shared_trajectory
