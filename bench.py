@@ -177,6 +177,8 @@ def main():
         from oracle import cpu_baseline
 
         cpu = cpu_baseline.run(args.workload, args.cpu_seconds, os.cpu_count() or 1)
+        # beside the faithful (scalar Python, like the reference) port: the same arithmetic compiled
+        cpu["compiled"] = cpu_baseline.run_compiled(args.workload, min(2.0, args.cpu_seconds))
 
     # pin this rank to the CPUs / NUMA node next to its GPU before any pinned host buffer exists,
     # so that the end-to-end leg's DMA targets local memory (matters at N > 1)

@@ -99,3 +99,81 @@ class Runner:
     def close(self):
         self.pool.close()
         self.pool.join()
+
+
+def _compiled_worker(args):
+    """The same workload through the COMPILED restatement (oracle/mbe_oracle_c.c): E envs per call,
+    one env per OpenMP iteration on all host threads."""
+    workload, seconds, envs = args
+    from oracle.c_oracle import CEnvBatch
+
+    bs, U, mode, handler, vel = WORKLOADS[workload]
+    p = orc.Params(velocity=vel)
+    rng = np.random.default_rng(7)
+    E = envs
+    if bs is None:  # the fork's scenario: 5..10 random BSs per env (custom.py:68-77)
+        layout = rng.integers(0, 200, size=(E, 10, 2)).astype(np.int32)
+        env = CEnvBatch(p, layout, E, U, nbs=rng.integers(5, 11, size=E))
+    else:
+        env = CEnvBatch(p, bs, E, U, handler=handler)
+    B = env.B
+    pool_wp = [rng.integers(0, int(p.width), size=(E, U, 2)).astype(np.int32) for _ in range(4)]
+    pool_act = [rng.integers(0, B + 1, size=(E, U)).astype(np.int32) for _ in range(4)]
+
+    def fresh():
+        env.reset(rng.integers(0, int(p.width), size=(E, U, 2)))
+
+    fresh()
+    calls = 0
+    t0 = time.perf_counter()
+    while True:
+        if mode == "gym":
+            env.step_gym(pool_act[calls % 4], pool_wp[calls % 4])
+        else:
+            env.step_fork(pool_wp[calls % 4])
+        calls += 1
+        if env.done[0]:
+            fresh()
+        if time.perf_counter() - t0 >= seconds:
+            break
+    return calls * E, time.perf_counter() - t0
+
+
+def run_compiled(workload: str, seconds: float = 2.0, envs: int = 8192):
+    """env-steps/s of the compiled C restatement on all host threads (OpenMP), or None when the
+    workload is outside what it covers.  Runs in a child process with a time-out (keeps libgomp out of
+    the caller; a missing compiler or a crash can never break or hang the bench line)."""
+    import json
+    import subprocess
+    import sys
+
+    if workload not in WORKLOADS:
+        return None
+    threads = os.cpu_count() or 1
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        res = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", "compiled", workload, str(seconds), str(envs)],
+                             cwd=root, capture_output=True, text=True, timeout=seconds + 120)
+        if res.returncode != 0:
+            raise RuntimeError(res.stderr.strip().splitlines()[-1] if res.stderr.strip() else f"exit {res.returncode}")
+        steps, wall = json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+    return {
+        "value": steps / wall, "unit": "env-steps/s", "cores": threads, "kind": "port (compiled C, OpenMP)",
+        "sample": f"{envs} envs x {steps // envs} steps of {workload} in {wall:.2f} s through oracle/mbe_oracle_c.c "
+                  f"(FP64, the reference's arithmetic per UE x BS pair, one env per OpenMP iteration)",
+    }
+
+
+if __name__ == "__main__":
+    import json
+    import sys
+
+    if len(sys.argv) == 5 and sys.argv[1] == "compiled":
+        from oracle import c_oracle
+
+        c_oracle.build()
+        print(json.dumps(_compiled_worker((sys.argv[2], float(sys.argv[3]), int(sys.argv[4])))))
+    else:
+        print(json.dumps(run(sys.argv[1] if len(sys.argv) > 1 else "mobile-medium-central-v0", 2.0)))
