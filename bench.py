@@ -135,6 +135,9 @@ def run_reference(args, rank, world):
             vals.append(r)
     runner.close()
     value = statistics.mean(v["value"] for v in vals)
+    # for transparency only (`value` stays the reference's own speed class, scalar Python): the same
+    # arithmetic as a compiled C + OpenMP restatement on the same cores
+    compiled = cpu_baseline.run_compiled(workload, 2.0)
     B, U = SIZES[workload.rsplit("-", 2)[0]]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -143,7 +146,7 @@ def run_reference(args, rank, world):
         "config": {"workload": workload, "envs_per_gpu": args.envs, "bs": B, "ues": U,
                    "note": "each step = every host core stepping its own env for a bounded time"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
-                         "sample": vals[-1]["sample"], "single_core": vals[-1]["single_core"]},
+                         "sample": vals[-1]["sample"], "single_core": vals[-1]["single_core"], "compiled": compiled},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
