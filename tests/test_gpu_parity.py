@@ -506,6 +506,74 @@ def test_channel_kernel_matches_oracle():
 
 
 # ------------------------------------------------------------------------- full size
+def _few_rounding_flips(got, want, what, max_flips=4):
+    """Rates are two-decimal roundings of FP64 values whose last ulp may differ between the host-folded
+    table (numpy) and the C restatement (glibc): equal except for at most a handful of 0.01 flips."""
+    diff = np.abs(np.asarray(got) - np.asarray(want))
+    assert int((diff > 0).sum()) <= max_flips and float(diff.max(initial=0.0)) <= 0.0100001, what
+
+
+@pytest.mark.parametrize("env_id,E", [("mobile-medium-central-v0", 65536), ("mobile-medium-ma-v0", 131072)])
+def test_full_size_gym_episode_matches_compiled_oracle(env_id, E):
+    """BASELINE configs[1] / configs[2] at FULL size against the compiled restatement of the reference's
+    arithmetic (oracle/mbe_oracle_c.c, pinned to the reference fixtures by tests/test_c_oracle.py): a
+    whole Philox-driven episode of every env -- connection sets, positions and done exact, rates exact up
+    to rounding flips, utilities / rewards / observations to 1e-5."""
+    import mobile_env_gan_b200 as mbe
+    from oracle.c_oracle import CEnvBatch
+
+    env = mbe.make(env_id, num_envs=E)
+    mir = Mirror(env)
+    env.reset()
+    mir._reinit(np.ones(E, dtype=bool))
+    U, B = mir.U, mir.B
+    assert np.array_equal(env.pos.cpu().numpy(), mir.pos)
+    c = CEnvBatch(mir.p, mir.bs, E, U, handler=mir.handler)
+    c.reset(mir.pos)
+    rng = np.random.default_rng(E)
+    for k in range(env.plan.ep_time):
+        acts = rng.integers(0, B + 1, size=(E, U)).astype(np.int32)
+        mir.t = c.t.astype(np.int64)
+        c.step_gym(acts, mir.new_wp())
+        obs, rew, _, trunc, _ = env.step(torch.from_numpy(acts).to(env.device))
+        assert np.array_equal(conn_bool_from_words(env.conn.cpu().numpy(), B), c.conn.astype(bool)), k
+        assert np.array_equal(env.pos.cpu().numpy(), c.pos), k
+        assert np.array_equal(trunc.cpu().numpy(), c.done.astype(bool)), k
+        _few_rounding_flips(env.rate.cpu().numpy(), c.rate, f"rate step {k}")
+        close(env.utility_scaled.cpu(), c.util, f"utility {k}")
+        close(rew.cpu(), c.reward, f"reward {k}")
+        close(obs.cpu().numpy().reshape(E, U, -1), c.obs, f"obs {k}")
+    assert bool(trunc.all())
+
+
+def test_full_size_fork_custom_episode_matches_compiled_oracle():
+    """The fork's own scenario at 262,144 envs (random per-env layouts, shared UE trajectory): a whole
+    episode against the compiled restatement -- association, positions, done exact, rates up to flips."""
+    from mobile_env_gan_b200.scenarios.custom import MComCustom
+    from oracle.c_oracle import CEnvBatch
+
+    E = 262144
+    env = MComCustom(config={"num_envs": E})
+    mir = Mirror(env)
+    env.reset()
+    mir._reinit(np.ones(E, dtype=bool))
+    assert np.array_equal(env.bs_xy.cpu().numpy(), mir.bs) and np.array_equal(env.nbs.cpu().numpy(), mir.nbs)
+    c = CEnvBatch(mir.p, mir.bs, E, mir.U, nbs=mir.nbs)
+    c.reset(mir.pos)
+    for k in range(env.plan.ep_time):
+        mir.t = c.t.astype(np.int64)
+        c.step_fork(mir.new_wp())
+        env.step(0, k)
+        assert np.array_equal(env.assoc.cpu().numpy(), c.assoc), k
+        assert np.array_equal(env.pos.cpu().numpy(), c.pos), k
+        assert np.array_equal(env.done.cpu().numpy(), c.done), k
+        _few_rounding_flips(env.rate.cpu().numpy(), c.rate, f"rate step {k}")
+        close(env.utility_scaled.cpu(), c.util, f"utility {k}")
+        m = env.metrics.cpu().numpy()
+        assert np.array_equal(m[:, 1], c.metrics[:, 1]), k
+    assert bool(env.done.all())
+
+
 def test_full_size_medium_properties_and_sharding():
     """BASELINE configs[1] size (65,536 envs): sharded halves reproduce the whole, and the
     size-independent invariants of the domain hold."""
