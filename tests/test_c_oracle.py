@@ -96,3 +96,71 @@ def test_compiled_cpu_baseline_runs_bounded():
     assert cpu_baseline.run_compiled("mobile-synthetic-central-v0", 0.2) is None  # ProportionalFair: not covered
     bad = cpu_baseline.run_compiled("mobile-small-central-v0", 0.2, envs=-5)
     assert "unavailable" in bad
+
+
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=20, deadline=None)
+@given(seed=st.integers(0, 10**6), U=st.integers(1, 12), B=st.integers(1, 8),
+       v=st.sampled_from([0.5, 1.5, 2.5, 7.3, 10.0, 40.0]), handler=st.sampled_from(["central", "ma"]))
+def test_c_and_python_oracles_agree_on_random_gym_episodes(seed, U, B, v, handler):
+    """Two independent restatements (compiled C / scalar Python) on random scenarios: GYM step incl.
+    observations and rewards."""
+    from oracle.c_oracle import CEnvBatch
+
+    rng = np.random.default_rng(seed)
+    p = orc.Params(velocity=v, ep_time=7, tx=float(rng.choice([30, 40, 46])), snr_tr=float(rng.choice([2e-8, 2e-7])))
+    bs = rng.integers(0, 200, size=(B, 2)).tolist()
+    init = rng.integers(0, 200, size=(U, 2)).tolist()
+    wps = rng.integers(0, 200, size=(U, 16, 2)).tolist()
+    py = orc.ScalarEnv(p, bs, U, wp_source=lambda u, k: wps[u][k])
+    py.reset(init)
+    c = CEnvBatch(p, bs, 2, U, handler=handler)
+    c.reset(init)
+    used = [0] * U
+    for _ in range(7):
+        acts = rng.integers(0, B + 1, size=U).tolist()
+        obs, rew, done, info = py.step_gym(acts, handler)
+        c.step_gym(acts, [wps[u][used[u]] for u in range(U)])
+        used = [used[u] + int(c.drew[0, u]) for u in range(U)]
+        for e in range(2):
+            want_conn = [[] for _ in range(U)] if done else info["conn"]
+            assert [np.flatnonzero(x).tolist() for x in c.conn[e]] == want_conn
+            assert c.pos[e].tolist() == [list(q) for q in info["pos"]] and bool(c.done[e]) == done
+            np.testing.assert_allclose(c.rate[e], info["rate"], rtol=1e-12, atol=0)
+            np.testing.assert_allclose(c.util[e], info["utility"], rtol=1e-12, atol=1e-15)
+            np.testing.assert_allclose(c.bs_util[e], info["bs_utility"], rtol=1e-12, atol=1e-15)
+            np.testing.assert_allclose(c.obs[e], obs, rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(np.ravel(c.reward[e]), np.ravel(rew), rtol=1e-12, atol=1e-15)
+
+
+@settings(max_examples=15, deadline=None)
+@given(seed=st.integers(0, 10**6), U=st.integers(1, 9), v=st.sampled_from([1.5, 4.0, 10.0, 25.0]))
+def test_c_and_python_oracles_agree_on_random_fork_layouts(seed, U, v):
+    """FORK step on per-env layouts with 1..10 live BS slots (the fork's MComCustom shape)."""
+    from oracle.c_oracle import CEnvBatch
+
+    rng = np.random.default_rng(seed)
+    E, B = 4, 10
+    p = orc.Params(velocity=v, ep_time=6)
+    nbs = rng.integers(1, B + 1, size=E)
+    layout = rng.integers(0, 200, size=(E, B, 2))
+    init = rng.integers(0, 200, size=(E, U, 2))
+    c = CEnvBatch(p, layout, E, U, nbs=nbs)
+    c.reset(init)
+    pys = []
+    for e in range(E):
+        env = orc.ScalarEnv(p, layout[e, : nbs[e]].tolist(), U)
+        env.reset(init[e].tolist())
+        pys.append(env)
+    for _ in range(6):
+        new_wp = rng.integers(0, 200, size=(E, U, 2))
+        c.step_fork(new_wp)
+        for e, env in enumerate(pys):
+            env.wp_source = lambda u, k, e=e: new_wp[e, u]
+            out = env.step_fork()
+            assert c.assoc[e].tolist() == out["assoc"] and c.pos[e].tolist() == [list(q) for q in out["pos"]]
+            np.testing.assert_allclose(c.rate[e], out["rate"], rtol=1e-12, atol=0)
+            np.testing.assert_allclose(c.util[e], out["utility"], rtol=1e-12, atol=1e-15)
+            assert bool(c.done[e]) == out["done"] and c.metrics[e][1] == out["n_connected"]
