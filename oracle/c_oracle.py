@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "_build", "libmbe_oracle_c.so")
 class CParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("width", "height", "velocity", "snr_tr", "noise", "ue_height",
                                           "util_lower", "util_upper", "w1", "w2", "w3")] + [
-        ("ep_time", C.c_int32), ("handler", C.c_int32)]
+        ("ep_time", C.c_int32), ("handler", C.c_int32), ("scheduler", C.c_int32), ("pad_", C.c_int32)]
 
 
 def build(force: bool = False) -> str:
@@ -53,8 +53,7 @@ class CEnvBatch:
     overrides like the fixtures hold (keys bw / freq / tx / bs_height)."""
 
     def __init__(self, p, bs_xy, num_envs, num_ues, handler="central", bs_over=None, nbs=None):
-        if p.scheduler != "resource_fair":
-            raise NotImplementedError("the C restatement covers ResourceFair (the reference's scheduler)")
+        sched = {"resource_fair": 0, "proportional_fair": 1, "rate_fair": 2}[p.scheduler]
         self.lib = load()
         bs_xy = np.asarray(bs_xy, dtype=np.int32)
         self.per_env = bs_xy.ndim == 3
@@ -65,7 +64,7 @@ class CEnvBatch:
         w1, w2, w3 = p.util_coeffs
         self.ma = handler != "central"
         self.cp = CParams(p.width, p.height, p.velocity, p.snr_tr, p.noise, p.ue_height, p.util_lower, p.util_upper,
-                          w1, w2, w3, int(p.ep_time), int(self.ma))
+                          w1, w2, w3, int(p.ep_time), int(self.ma), sched, 0)
         par = np.tile(np.array([p.bw, p.freq, p.tx, p.bs_height], dtype=np.float64), (self.B, 1))
         for b, over in enumerate(bs_over or []):
             for k, v in (over or {}).items():

@@ -16,7 +16,8 @@
  *   base.py:212-214        check_connectivity (snr > threshold, strict)
  *   base.py:236-241        FORK association: nearest connectable BS, first minimum wins
  *   base.py:221-227        update_connections (GYM)
- *   base.py:421-435        allocateDataRate2User: ResourceFair share (schedules.py:20-22), round(.,2)
+ *   base.py:421-435        allocateDataRate2User: ResourceFair share (schedules.py:20-22), round(.,2);
+ *                          ProportionalFair / repaired RateFair as specified in oracle/mbe_oracle.py
  *   base.py:413-418        user_total_datarates (bs-major sum)
  *   utilities.py:44-55     BoundedLogUtility calculate / scale
  *   base.py:438-447        allStationUtilities;  metrics.py:5-28 monitor scalars
@@ -39,7 +40,10 @@ typedef struct {
   double width, height, velocity, snr_tr, noise, ue_height;
   double util_lower, util_upper, w1, w2, w3;
   int32_t ep_time;
-  int32_t handler; /* 0 central, 1 multi-agent (GYM observations / reward) */
+  int32_t handler;   /* 0 central, 1 multi-agent (GYM observations / reward) */
+  int32_t scheduler; /* 0 ResourceFair (schedules.py:20-22); 1 ProportionalFair, 2 repaired RateFair: this
+                        build's own specifications (oracle/mbe_oracle.py pf_total / rate_fair_share) */
+  int32_t pad_;
 } mbo_params;
 
 typedef struct {
@@ -67,6 +71,19 @@ static inline double datarate(const mbo_params* p, const bs_fold* f, double snr)
 }
 
 static inline double round2(double v) { return rint(v * 100.0) / 100.0; } /* np.float64.__round__(2) */
+
+/* Order-independent per-BS totals of the two extra schedulers (fixed point, exact integer sums):
+ * ProportionalFair  total = sum(rint(r * 2^20)) * 2^-20,   share_u = r_u * r_u / total
+ * RateFair          total = sum(rint(2^50 / r)) * 2^-50,   share   = 1 / total */
+typedef unsigned __int128 fix_t;
+static inline fix_t sched_term(int scheduler, double r) {
+  return scheduler == 1 ? (fix_t)rint(r * 1048576.0) : scheduler == 2 ? (fix_t)rint(0x1p50 / r) : (fix_t)0;
+}
+static inline double link_share(int scheduler, double r, int n, fix_t tot) {
+  if (scheduler == 1) return (r * r) / ((double)tot * (1.0 / 1048576.0));
+  if (scheduler == 2) return 1.0 / ((double)tot * 0x1p-50);
+  return r / (double)n;
+}
 
 static inline double scaled_utility(const mbo_params* p, double rate) {
   double u = p->util_lower;
@@ -147,10 +164,17 @@ void mbo_fork_step(const mbo_params* p, int E, int U, int B, const double* bs_pa
     }
     int nconn = 0;
     double usum = 0.0, rsum = 0.0;
+    fix_t tot[MBO_MAX_B];
+    if (p->scheduler) {
+      memset(tot, 0, sizeof(fix_t) * (size_t)B);
+      for (int u = 0; u < U; ++u)
+        if (as[u] >= 0) tot[as[u]] += sched_term(p->scheduler, datarate(p, &fold[as[u]], best_snr[u]));
+    }
     for (int u = 0; u < U; ++u) { /* base.py:421-435, 413-418, 253-258 */
       double r = 0.0;
       if (as[u] >= 0) {
-        r = 0.0 + round2(datarate(p, &fold[as[u]], best_snr[u]) / (double)cnt[as[u]]);
+        r = 0.0 + round2(link_share(p->scheduler, datarate(p, &fold[as[u]], best_snr[u]), cnt[as[u]],
+                                    p->scheduler ? tot[as[u]] : (fix_t)0));
         nconn += 1;
         rsum += r;
       }
@@ -218,12 +242,19 @@ void mbo_gym_step(const mbo_params* p, int E, int U, int B, const double* bs_par
       nlinks += cnt[b];
     }
     double usum = 0.0, rsum = 0.0;
+    fix_t tot[MBO_MAX_B];
+    for (int b = 0; b < B; ++b) {
+      tot[b] = 0;
+      if (p->scheduler)
+        for (int u = 0; u < U; ++u)
+          if (cn[u * B + b]) tot[b] += sched_term(p->scheduler, datarate(p, &fold[b], snr[u * B + b]));
+    }
     for (int u = 0; u < U; ++u) {
       double r = 0.0;
       int any = 0;
       for (int b = 0; b < B; ++b)
         if (cn[u * B + b]) {
-          r += round2(datarate(p, &fold[b], snr[u * B + b]) / (double)cnt[b]);
+          r += round2(link_share(p->scheduler, datarate(p, &fold[b], snr[u * B + b]), cnt[b], tot[b]));
           any = 1;
         }
       rt[u] = r;

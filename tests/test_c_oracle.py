@@ -64,7 +64,7 @@ def test_c_gym_step_replays_reference_primitive_episodes(name, handler):
                 assert env.reward[e] == pytest.approx(float(np.mean(g["utility"])), rel=1e-12, abs=1e-15)
 
 
-@pytest.mark.parametrize("name", ["central_rf", "ma_rf"])
+@pytest.mark.parametrize("name", ["central_rf", "ma_rf", "ma_pf"])
 def test_c_gym_step_matches_the_frozen_spec_vectors(name):
     """Observations and rewards (this build's GYM spec, frozen from the Python oracle)."""
     from oracle.c_oracle import CEnvBatch
@@ -93,7 +93,7 @@ def test_compiled_cpu_baseline_runs_bounded():
 
     out = cpu_baseline.run_compiled("mobile-small-central-v0", 0.2, envs=256)
     assert out["value"] > 0 and out["kind"].startswith("port (compiled C") and out["cores"] >= 1
-    assert cpu_baseline.run_compiled("mobile-synthetic-central-v0", 0.2) is None  # ProportionalFair: not covered
+    assert cpu_baseline.run_compiled("mobile-synthetic-central-v0", 0.2) is None  # not in the baseline's workload table
     bad = cpu_baseline.run_compiled("mobile-small-central-v0", 0.2, envs=-5)
     assert "unavailable" in bad
 
@@ -103,14 +103,16 @@ from hypothesis import given, settings, strategies as st  # noqa: E402
 
 @settings(max_examples=20, deadline=None)
 @given(seed=st.integers(0, 10**6), U=st.integers(1, 12), B=st.integers(1, 8),
-       v=st.sampled_from([0.5, 1.5, 2.5, 7.3, 10.0, 40.0]), handler=st.sampled_from(["central", "ma"]))
-def test_c_and_python_oracles_agree_on_random_gym_episodes(seed, U, B, v, handler):
+       v=st.sampled_from([0.5, 1.5, 2.5, 7.3, 10.0, 40.0]), handler=st.sampled_from(["central", "ma"]),
+       sched=st.sampled_from(["resource_fair", "proportional_fair", "rate_fair"]))
+def test_c_and_python_oracles_agree_on_random_gym_episodes(seed, U, B, v, handler, sched):
     """Two independent restatements (compiled C / scalar Python) on random scenarios: GYM step incl.
     observations and rewards."""
     from oracle.c_oracle import CEnvBatch
 
     rng = np.random.default_rng(seed)
-    p = orc.Params(velocity=v, ep_time=7, tx=float(rng.choice([30, 40, 46])), snr_tr=float(rng.choice([2e-8, 2e-7])))
+    p = orc.Params(velocity=v, ep_time=7, tx=float(rng.choice([30, 40, 46])), snr_tr=float(rng.choice([2e-8, 2e-7])),
+                   scheduler=sched)
     bs = rng.integers(0, 200, size=(B, 2)).tolist()
     init = rng.integers(0, 200, size=(U, 2)).tolist()
     wps = rng.integers(0, 200, size=(U, 16, 2)).tolist()
