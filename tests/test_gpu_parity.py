@@ -755,6 +755,33 @@ def test_wide_gym_matches_oracle(name, handler):
         close(m[:, 3], out["mean_datarate"])
 
 
+def test_synthetic_shape_many_envs_matches_compiled_oracle():
+    """BASELINE configs[4] shape (64 BS x 512 UE, ProportionalFair) on 1,024 envs against the compiled
+    restatement (the numpy oracle above is limited to 24 envs by its speed): connection sets, positions,
+    done exact, rates up to rounding flips, utilities / reward / observations 1e-5."""
+    CEnvBatch = _compiled_oracle()
+    E = 1024
+    env, B, U = wide_env("synthetic", "gym", "central", E, autoreset=False)
+    mir = Mirror(env)
+    env.reset()
+    mir._reinit(np.ones(E, dtype=bool))
+    c = CEnvBatch(mir.p, mir.bs, E, U, handler="central")
+    c.reset(mir.pos)
+    rng = np.random.default_rng(3)
+    for k in range(3):
+        acts = rng.integers(0, B + 1, size=(E, U)).astype(np.int32)
+        mir.t = c.t.astype(np.int64)
+        c.step_gym(acts, mir.new_wp())
+        obs, rew, _, trunc, _ = env.step(torch.from_numpy(acts).to(env.device))
+        assert np.array_equal(conn_bool_from_words(env.conn.cpu().numpy(), B), c.conn.astype(bool)), k
+        assert np.array_equal(env.pos.cpu().numpy(), c.pos), k
+        assert np.array_equal(trunc.cpu().numpy(), c.done.astype(bool)), k
+        _few_rounding_flips(env.rate.cpu().numpy(), c.rate, f"rate step {k}", max_flips=8)
+        close(env.utility_scaled.cpu(), c.util, f"utility {k}")
+        close(rew.cpu(), c.reward, f"reward {k}")
+        close(obs.cpu().numpy().reshape(E, U, -1), c.obs, f"obs {k}")
+
+
 @pytest.mark.parametrize("name", ["wide_rf", "wide_pf", "many_ue"])
 def test_wide_fork_matches_oracle(name):
     E = 40
