@@ -431,8 +431,8 @@ def main():
                 "traffic_note": "ncu dram bytes of ONE cold launch: reads = the algorithmic state+action bytes; most "
                                 "output bytes were still dirty in the 126 MB L2 when the profiled launch ended "
                                 "(profiles/step_kernel_traffic.json)",
-                "peak_source": peak_src, "kernel": (f"mbe::step_upt_kernel<{handler},U={U},B={B},K=5>" if (U, B) == (15, 4) and not fork else
-                           f"mbe::step_spec_kernel<{'fork' if fork else 'gym'},{handler},U={U},B={B}>" if U <= 32 and B <= 32 else f"mbe::step_big_kernel<gym,{handler}> U={U} B={B}"),
+                "peak_source": peak_src,
+                "kernel": f"mbe::{envs[0].step_kernel_name}<{'fork' if fork else 'gym'},{handler},U={U},B={B}>",
                 "bytes_per_env_step": bpe["layout"], "bytes_per_env_step_survey_8d": bpe["survey_8d"],
                 "frac_survey_8d": bpe["survey_8d"] * E / per_launch_s / 1e9 / peak,
             },

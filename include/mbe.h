@@ -202,6 +202,11 @@ int mbe_rollout(mbe_env* env, int steps, float* qoe_acc, float threshold, const 
 /* number of kernel launches this handle has enqueued so far */
 int64_t mbe_launch_count(const mbe_env* env);
 
+/* which kernel family mbe_step dispatches to for this handle's shape and bound buffers, e.g.
+ * "step_upt_kernel" (several UEs per thread), "step_spec_kernel" (warp segment, compile-time shape),
+ * "step_tpe_fork_kernel" (thread per env), "step_big_kernel" (block per env), "step_kernel" (generic) */
+const char* mbe_step_kernel_name(const mbe_env* env);
+
 /* Host-buffer convenience: H2D actions, step, D2H obs/reward/done, then synchronises the
  * stream.  Host pointers should be pinned.  NULL pointers are skipped.  Large batches with
  * observations are processed as env windows on two streams so uploads and the step overlap the

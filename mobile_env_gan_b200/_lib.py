@@ -115,6 +115,7 @@ SYMBOLS = [
     ("mbe_accumulate_qoe", C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     ("mbe_rollout", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.POINTER(RolloutOut), C.c_void_p]),
     ("mbe_launch_count", C.c_int64, [C.c_void_p]),
+    ("mbe_step_kernel_name", C.c_char_p, [C.c_void_p]),
     ("mbe_step_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 ]
 

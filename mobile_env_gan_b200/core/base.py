@@ -469,6 +469,11 @@ class MComCore:
         return int(self._lib.mbe_launch_count(self._handle))
 
     @property
+    def step_kernel_name(self) -> str:
+        """The kernel family ``step`` dispatches to for this shape (``mbe_step_kernel_name``)."""
+        return self._lib.mbe_step_kernel_name(self._handle).decode()
+
+    @property
     def time_is_up(self):
         """base.py:407-409, per env."""
         return self.done.view(torch.bool)

@@ -695,6 +695,15 @@ int mbe_rollout(mbe_env* env, int steps, float* qoe_acc, float threshold, const 
 
 int64_t mbe_launch_count(const mbe_env* env) { return env ? env->launches : 0; }
 
+const char* mbe_step_kernel_name(const mbe_env* env) {  // mirrors the dispatch order of launch()
+  if (!env) return "";
+  if (env->big) return "step_big_kernel";
+  if (env->tpe && (!env->bound || env->tpe_bound_ok) && !env->args.dbg_snr) return "step_tpe_fork_kernel";
+  if (env->upt && !env->args.dbg_snr) return "step_upt_kernel";
+  if (env->spec && !env->args.dbg_snr) return env->pipe ? "step_pipe_kernel" : "step_spec_kernel";
+  return "step_kernel";
+}
+
 int mbe_step_host(mbe_env* env, const int32_t* actions_host, float* obs_host, float* reward_host,
                   uint8_t* done_host, void* stream) {
   if (!env) return fail("null handle");

@@ -333,3 +333,16 @@ def test_bs_isolines_uses_the_reference_outline():
     assert len(lines) == 3
     xs, ys = lines[env.stationDict[0]]
     assert list(map(float, xs)) == case["xs"] and list(map(float, ys)) == case["ys"]
+
+
+def test_step_kernel_name_reports_the_dispatched_family():
+    import mobile_env_gan_b200 as mbe
+    from mobile_env_gan_b200.scenarios.custom import MComCustom
+
+    assert mbe.make("mobile-medium-central-v0", num_envs=64).step_kernel_name == "step_upt_kernel"
+    assert mbe.make("mobile-large-ma-v0", num_envs=64).step_kernel_name == "step_spec_kernel"
+    assert mbe.make("mobile-synthetic-central-v0", num_envs=4).step_kernel_name == "step_big_kernel"
+    assert MComCustom(config={"num_envs": 64}).step_kernel_name == "step_tpe_fork_kernel"
+    assert MComCustom(config={"num_envs": 40}).step_kernel_name == "step_spec_kernel"  # E % 32 != 0
+    generic = mbe.make("mobile-medium-central-v0", num_envs=64, config={"generic_kernel": True})
+    assert generic.step_kernel_name == "step_kernel"
