@@ -1,7 +1,7 @@
 """Reference-named host view of one environment (slow path, for inspection and export)."""
 from __future__ import annotations
 
-from collections import defaultdict
+from collections import Counter, defaultdict
 
 from .entities import BaseStation, UserEquipment
 
@@ -12,6 +12,7 @@ class EnvView:
     def __init__(self, env, e: int):
         p = env.plan
         cfg = env.config
+        self.channelModel, self.schedulerModel, self.utilityModel = env.channelModel, env.schedulerModel, env.utilityModel
         pos = env.pos[e].cpu().tolist()
         if env.nbs is None:
             bs_xy, nbs = env.bs_xy.cpu().tolist(), p.num_bs
@@ -51,3 +52,44 @@ class EnvView:
         self.stations, self.users, self.active = self.stationDict, self.userDict, self.activeUsers
         self.connections, self.datarates = self.bs2ue_connections, self.bs2ue_dataRates
         self.macro, self.utilities = self.allUserDataRates, self.ue_utilities
+
+    # ---- the reference's per-entity queries on this snapshot (scalar host code, like base.py) ----
+    def check_connectivity(self, bs, ue) -> bool:
+        """``snr > snr_threshold`` for one link (reference base.py:212-214)."""
+        return self.channelModel.calculateSNR(bs, ue) > ue.snr_threshold
+
+    def available_connections(self, ue) -> set:
+        """The stations ``ue`` could connect to (reference base.py:216-218)."""
+        return {bs for bs in self.stationDict.values() if self.check_connectivity(bs, ue)}
+
+    def update_connections(self) -> None:
+        """Keeps only the links that still pass ``check_connectivity`` (reference base.py:221-227)."""
+        kept = {bs: {ue for ue in ues if self.check_connectivity(bs, ue)} for bs, ues in self.bs2ue_connections.items()}
+        self.bs2ue_connections.clear()
+        self.bs2ue_connections.update(kept)
+
+    def allocateDataRate2User(self, bs) -> dict:
+        """``{(bs, ue): rate}`` of one station: scheduler share of the Shannon rates, two decimals
+        (reference base.py:421-435)."""
+        ues = list(self.bs2ue_connections.get(bs, ()))
+        snrs = [self.channelModel.calculateSNR(bs, ue) for ue in ues]
+        caps = [self.channelModel.datarate(bs, ue, snr) for ue, snr in zip(ues, snrs)]
+        shares = self.schedulerModel.share(bs, caps) if ues else []
+        return {(bs, ue): round(rate, 2) for ue, rate in zip(ues, shares)}
+
+    def user_total_datarates(self, bs2ue_dataRates) -> Counter:
+        """Per-UE sum over its links (reference base.py:413-418)."""
+        totals = Counter()
+        for (_, ue), rate in bs2ue_dataRates.items():
+            totals.update({ue: rate})
+        return totals
+
+    def allStationUtilities(self) -> dict:
+        """Mean utility of every station's UEs, the scaled lower bound for an idle one (reference
+        base.py:438-447)."""
+        idle = self.utilityModel.scaleUtility(self.utilityModel.lower)
+        out = {}
+        for bs in self.stationDict.values():
+            ues = self.bs2ue_connections.get(bs)
+            out[bs] = sum(self.ue_utilities[ue] for ue in ues) / len(ues) if ues else idle
+        return out

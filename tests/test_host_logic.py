@@ -308,3 +308,71 @@ def test_shared_trajectory_follows_the_forks_movement_flag():
     bs = [BaseStation(0, (10, 10), **MComCore.default_config()["bs"])]
     assert not plan_of(MComCore, {"num_envs": 64}, bs).shared_trajectory
     assert plan_of(MComCore, {"num_envs": 64, "shared_trajectory": True}, bs).shared_trajectory
+
+
+def test_env_view_queries_match_the_reference_methods():
+    """EnvView.check_connectivity / available_connections / allocateDataRate2User / user_total_datarates /
+    allStationUtilities / update_connections (reference base.py:212-227, 413-447) on a snapshot, against
+    the reference's own methods on the same state (a GYM-order episode with UEs on several BSs)."""
+    import types
+
+    import torch
+
+    from oracle import ref_harness
+
+    if not ref_harness.reference_available():
+        pytest.skip("the reference is only importable in the build container")
+    from mobile_env_gan_b200.core.schedules import ResourceFair
+    from mobile_env_gan_b200.core.utilities import BoundedLogUtility
+    from mobile_env_gan_b200.core.views import EnvView
+
+    bs_xy, U = [(50, 50), (150, 50), (50, 150), (150, 150)], 9
+    ref = ref_harness.make_fixed_layout_env(bs_xy, U, config={"ue": {"velocity": 6}})
+    rng = np.random.default_rng(4)
+    actions = rng.integers(0, 5, size=(6, U)).tolist()
+    ref_harness.record_gym_pieces_episode(ref, actions)  # leaves the reference env in its final state
+    r_bss = [ref.stationDict[k] for k in sorted(ref.stationDict)]
+    r_ues = [ref.userDict[k] for k in sorted(ref.userDict)]
+    # the same state as a batched-env snapshot (CPU tensors are enough for the view)
+    cfg = MComCore.seeding(deep_dict_merge(MComCore.default_config(), {"ue": {"velocity": 6}, "mode": "gym"}))
+    stations = [BaseStation(i, xy, **cfg["bs"]) for i, xy in enumerate(bs_xy)]
+    users = [UserEquipment(i, **cfg["ue"]) for i in range(U)]
+    conn = torch.tensor([[sum(1 << b.bs_id for b in r_bss if ue in ref.bs2ue_connections[b]) for ue in r_ues]])
+    stub = types.SimpleNamespace(
+        plan=MComCore.build_plan(stations, users, cfg), config=cfg,
+        channelModel=OkumuraHata(), schedulerModel=ResourceFair(),
+        utilityModel=BoundedLogUtility(**cfg["utility_params"]),
+        pos=torch.tensor([[[int(ue.x), int(ue.y)] for ue in r_ues]]), bs_xy=torch.tensor(bs_xy), nbs=None,
+        stationDict={b.bs_id: b for b in stations}, userDict={u.ue_id: u for u in users},
+        t=torch.tensor([int(ref.time)]), rate=torch.tensor([[float(ref.allUserDataRates.get(ue, 0.0)) for ue in r_ues]]),
+        utility_scaled=torch.tensor([[float(ref.ue_utilities[ue]) for ue in r_ues]], dtype=torch.float64),
+        assoc=None, conn=conn)
+    view = EnvView(stub, 0)
+    v_bss, v_ues = [view.stationDict[i] for i in range(4)], [view.userDict[i] for i in range(U)]
+    ids = lambda s: sorted(x.bs_id if hasattr(x, "bs_id") else x.ue_id for x in s)  # noqa: E731
+    multi = 0
+    for vu, ru in zip(v_ues, r_ues):
+        assert ids(view.available_connections(vu)) == ids(ref.available_connections(ru))
+        for vb, rb in zip(v_bss, r_bss):
+            assert view.check_connectivity(vb, vu) == ref.check_connectivity(rb, ru)
+        multi += sum(vu in view.bs2ue_connections[vb] for vb in v_bss) > 1
+    assert multi > 0
+    all_rates = {}
+    for vb, rb in zip(v_bss, r_bss):
+        got = {(b.bs_id, u.ue_id): r for (b, u), r in view.allocateDataRate2User(vb).items()}
+        want = {(b.bs_id, u.ue_id): r for (b, u), r in ref.allocateDataRate2User(rb).items()}
+        assert got == want
+        all_rates.update(view.allocateDataRate2User(vb))
+    got_tot = {u.ue_id: r for u, r in view.user_total_datarates(all_rates).items()}
+    ref_rates = {}
+    for rb in r_bss:
+        ref_rates.update(ref.allocateDataRate2User(rb))
+    assert got_tot == {u.ue_id: r for u, r in ref.user_total_datarates(ref_rates).items()}
+    got_u = {b.bs_id: v for b, v in view.allStationUtilities().items()}
+    want_u = {b.bs_id: v for b, v in ref.allStationUtilities().items()}
+    assert got_u.keys() == want_u.keys() and all(got_u[k] == pytest.approx(want_u[k], rel=1e-12) for k in got_u)
+    # move everybody far away: update_connections drops every link on both sides
+    for vu, ru in zip(v_ues, r_ues):
+        vu.x = ru.x = 5000
+    view.update_connections(), ref.update_connections()
+    assert all(len(view.bs2ue_connections[b]) == 0 for b in v_bss) and all(len(ref.bs2ue_connections[b]) == 0 for b in r_bss)
