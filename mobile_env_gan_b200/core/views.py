@@ -93,3 +93,30 @@ class EnvView:
             ues = self.bs2ue_connections.get(bs)
             out[bs] = sum(self.ue_utilities[ue] for ue in ues) / len(ues) if ues else idle
         return out
+
+    def save_layout_and_data_rates(self, epoch_number: int, curr_step: int, root: str = ".."):
+        """Writes this snapshot's four per-step JSON files exactly like the reference does from inside
+        ``step`` (base.py:298-349: ``../collectData/{BaseStationPosition,UserEquipmentPosition,DataRate,
+        UserQoE}/..._{epoch}_{step}.json``; ``root`` replaces the leading ``..``).  For whole batches
+        use ``export.ReferenceDumpWriter`` -- this is the one-env convenience with the reference's name."""
+        import os
+
+        from ..export import format_step_files
+
+        stations = [self.stationDict[k] for k in sorted(self.stationDict)]
+        users = [self.userDict[k] for k in sorted(self.userDict)]
+        assoc = [-1] * len(users)
+        for bs, ues in self.bs2ue_connections.items():
+            for ue in ues:
+                assoc[ue.ue_id] = bs.bs_id
+        rate = [self.allUserDataRates.get(ue, 0.0) for ue in users]
+        util = self.utilityModel
+        files = format_step_files(int(epoch_number), int(curr_step), [(bs.x, bs.y) for bs in stations],
+                                  [(ue.x, ue.y) for ue in users], assoc, rate,
+                                  (util.lower, util.upper, tuple(util.coeffs)))
+        for rel, text in files.items():
+            path = os.path.join(root, rel)
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            with open(path, "w") as f:
+                f.write(text)
+        return sorted(files)

@@ -160,3 +160,41 @@ def test_gpu_writer_rollout_equals_stepping_on_custom_scenario(tmp_path):
 
     a, b = run(tmp_path / "steps", False), run(tmp_path / "fused", True)
     assert len(a) == 3 * 84 and a == b
+
+
+def test_env_view_writes_the_reference_step_files(tmp_path):
+    """EnvView.save_layout_and_data_rates (the reference's method name, base.py:298-349) on snapshots of
+    the kat1 episode: the same bytes as the files the reference wrote."""
+    import types
+
+    import torch
+
+    from mobile_env_gan_b200.core.base import MComCore
+    from mobile_env_gan_b200.core.channels import OkumuraHata
+    from mobile_env_gan_b200.core.entities import BaseStation, UserEquipment
+    from mobile_env_gan_b200.core.schedules import ResourceFair
+    from mobile_env_gan_b200.core.util import deep_dict_merge
+    from mobile_env_gan_b200.core.utilities import BoundedLogUtility
+    from mobile_env_gan_b200.core.views import EnvView
+
+    rec, p, steps = replay_kat1()
+    pr = rec["params"]
+    cfg = MComCore.seeding(deep_dict_merge(MComCore.default_config(), {
+        "bs": {"tx": pr["tx"]}, "ue": {"velocity": pr["velocity"], "height": pr["ue_height"]}}))
+    stations = [BaseStation(i, tuple(xy), **cfg["bs"]) for i, xy in enumerate(rec["bs_xy"])]
+    users = [UserEquipment(i, **cfg["ue"]) for i in range(len(rec["init_pos"]))]
+    plan = MComCore.build_plan(stations, users, cfg)
+    n = 0
+    for k in (0, 7, 19):
+        st = steps[k]
+        stub = types.SimpleNamespace(
+            plan=plan, config=cfg, channelModel=OkumuraHata(), schedulerModel=ResourceFair(),
+            utilityModel=BoundedLogUtility(**cfg["utility_params"]),
+            pos=torch.tensor([st["pos"]]), bs_xy=torch.tensor(rec["bs_xy"]), nbs=None,
+            stationDict={b.bs_id: b for b in stations}, userDict={u.ue_id: u for u in users},
+            t=torch.tensor([k + 1]), rate=torch.tensor([st["rate"]], dtype=torch.float64),
+            utility_scaled=torch.zeros(1, len(users), dtype=torch.float64),
+            assoc=torch.tensor([st["assoc"]]), conn=None)
+        written = EnvView(stub, 0).save_layout_and_data_rates(0, k, root=str(tmp_path))
+        n += check_against_reference_files({rel: open(os.path.join(tmp_path, rel)).read() for rel in written})
+    assert n == 12
