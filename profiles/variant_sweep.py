@@ -7,7 +7,7 @@
                    -> one bench.py run per (variant, workload) through MBE_LIB_PATH, a table at the end
   afterwards:      python profiles/variant_sweep.py clean
 
-Every number in profiles/README.md's launch-bound tables was produced this way."""
+The launch-bound tables in profiles/README.md came from sweeps of this form."""
 import glob
 import itertools
 import json
