@@ -14,7 +14,10 @@ Printed JSON line (rank 0): value = whole-job env-steps/s with inputs resident i
 e2e = the same metric through the host-buffer C-ABI call (mbe_step_host: pinned host actions
 in, obs/reward/done out, copies inside the timed region); roofline = algorithmic bytes of the
 step kernel / its average duration against the measured HBM peak; cpu_baseline = the oracle's
-scalar port of the reference step timed on this box's host cores.
+scalar-Python port of the reference step timed on this box's host cores (the reference's own speed
+class), with ``cpu_baseline.compiled`` = the same arithmetic as a compiled C + OpenMP restatement.
+Secondary keys (never used for value / roofline): e2e.obs_stays_on_device, two_env_groups_in_flight,
+fused_episode (FORK workloads, mbe_rollout).
 """
 from __future__ import annotations
 
