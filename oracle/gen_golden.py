@@ -316,6 +316,40 @@ def custom_epochs_golden(epochs=4, steps=20, seed=123):
     print("custom_epochs", epochs, "epochs", [len(e["bs_xy"]) for e in out["epochs"]], "BSs")
 
 
+def custom_dump_golden(epochs=2, steps=20, seed=123):
+    """The fork's collect loop exactly as shipped (collectData2.ipynb: MComCustom, reset ->
+    save_base_station_positions -> 20 x step (dumping inside) -> save_epoch_data) with the global
+    ``random`` seeded like custom_epochs_golden, so epoch e here IS epoch e of custom_epochs.json.
+    Files -> tests/golden/dumps/custom/ (5..10 BSs per epoch: the station files of varying length)."""
+    import random
+    import shutil
+    import tempfile
+
+    base, entities, custom = rh.import_reference()
+    random.seed(seed)
+    env = custom.MComCustom()
+    tmp = tempfile.mkdtemp()
+    run = os.path.join(tmp, "run")
+    os.makedirs(run)
+    cwd = os.getcwd()
+    os.chdir(run)
+    try:
+        for ep in range(epochs):
+            env.reset()
+            env.save_base_station_positions(ep)
+            for s in range(steps):
+                env.step(ep, s)
+            env.save_epoch_data(ep)
+    finally:
+        os.chdir(cwd)
+    dst = os.path.join(OUT, "dumps", "custom")
+    shutil.rmtree(dst, ignore_errors=True)
+    for sub in ("collectData", "collectData2"):
+        shutil.copytree(os.path.join(tmp, sub), os.path.join(dst, sub))
+    shutil.rmtree(tmp)
+    print("dumps custom", sum(len(f) for _, _, f in os.walk(dst)), "files")
+
+
 def isoline_golden():
     """Coverage outlines from the reference's ``Channel.isoline`` (channels.py:30-75) for the default
     BS / UE parameters (base.py:117-123); rays that raise in the reference are recorded by exception
@@ -346,6 +380,7 @@ if __name__ == "__main__":
     main()
     dump_golden("kat1")
     custom_epochs_golden()
+    custom_dump_golden()
     isoline_golden()
     random_golden()
     gym_pieces_golden()

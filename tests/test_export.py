@@ -13,16 +13,17 @@ from oracle import mbe_oracle as orc
 DUMPS = os.path.join(GOLDEN_DIR, "dumps", "kat1")
 
 
-def read(rel):
-    with open(os.path.join(DUMPS, rel)) as f:
+def read(rel, root=DUMPS):
+    with open(os.path.join(root, rel)) as f:
         return f.read()
 
 
-def check_against_reference_files(files):
-    """files: {relative path: text} for epoch/env 0 of the kat1 episode."""
+def check_against_reference_files(files, root=DUMPS):
+    """files: {relative path: text}; root: the directory of files the reference wrote (default: epoch 0
+    of the kat1 episode)."""
     n = 0
     for rel, text in files.items():
-        ref = read(rel)
+        ref = read(rel, root)
         if os.sep + "DataRate" + os.sep + "data_rates_" in rel:
             # the reference lists the UEs of a BS in Python-set order; compare order-insensitively
             key = lambda d: (d["bs_id"], d["ue_id"])  # noqa: E731
@@ -198,3 +199,33 @@ def test_env_view_writes_the_reference_step_files(tmp_path):
         written = EnvView(stub, 0).save_layout_and_data_rates(0, k, root=str(tmp_path))
         n += check_against_reference_files({rel: open(os.path.join(tmp_path, rel)).read() for rel in written})
     assert n == 12
+
+
+def test_formatters_reproduce_the_shipped_collect_loop_files():
+    """The fork's collect loop as shipped (MComCustom: a fresh 5..10-BS layout per epoch, dumps written
+    from inside step / save_base_station_positions / save_epoch_data; tests/golden/dumps/custom from
+    oracle/gen_golden.py:custom_dump_golden) for two epochs, from the oracle's replay of
+    custom_epochs.json: every file byte for byte (168 files)."""
+    from mobile_env_gan_b200.export import format_epoch_files, format_step_files
+
+    root = os.path.join(GOLDEN_DIR, "dumps", "custom")
+    with open(os.path.join(GOLDEN_DIR, "custom_epochs.json")) as f:
+        epochs = json.load(f)["epochs"]
+    p = orc.Params(velocity=10.0)  # MComCustom: custom.py:17
+    util = (int(p.util_lower), int(p.util_upper), tuple(int(c) for c in p.util_coeffs))
+    n = 0
+    for e in (0, 1):
+        rec = epochs[e]
+        seq = golden_waypoints(rec)
+        env = orc.ScalarEnv(p, rec["bs_xy"], len(rec["init_pos"]), wp_source=lambda u, k: seq[u][k])
+        env.reset(rec["init_pos"])
+        steps = []
+        for s, g in enumerate(rec["steps"]):
+            out = env.step_fork()
+            assert [list(q) for q in out["pos"]] == g["pos"] and out["assoc"] == g["conn"]
+            steps.append({"pos": out["pos"], "arrived": [w is None for w in env.wp], "assoc": out["assoc"], "rate": out["rate"]})
+            n += check_against_reference_files(format_step_files(e, s, rec["bs_xy"], out["pos"], out["assoc"], out["rate"], util), root)
+        n += check_against_reference_files(format_epoch_files(
+            e, rec["bs_xy"], [st["pos"] for st in steps], [st["arrived"] for st in steps],
+            [st["assoc"] for st in steps], [st["rate"] for st in steps], util), root)
+    assert n == 168
