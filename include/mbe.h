@@ -15,9 +15,11 @@
  *   - return 0 on success, non-zero on error; mbe_last_error() gives a thread-local text;
  *   - one handle per device; a handle is not thread-safe, different handles are.
  *
- * Shapes: U <= 32 and B <= 32 run on the warp-segment kernels (one thread per UE, an env is a
- * slice of a warp); 32 < U <= 1024 or 32 < B <= 64, and the ProportionalFair / RateFair schedulers, run on the
- * block-per-env kernel (fused mbe_step / mbe_reset only; no mbe_stage / mbe_observe).
+ * Shapes: U <= 32 and B <= 32 run on the warp-segment kernels (an env is a slice of a warp; the
+ * scenario shapes have fused compile-time variants: several UEs per thread for 15 x 4, a thread per
+ * env for the fork's 7 UEs x 10 per-env BS slots -- mbe_step_kernel_name() tells which);
+ * 32 < U <= 1024 or 32 < B <= 64, and the ProportionalFair / RateFair schedulers, run on the
+ * block-per-env kernel (fused mbe_step / mbe_reset only; no mbe_stage / mbe_observe / mbe_step_window).
  *
  * Data layout (structure of arrays, env-major; E = envs on this rank, U = UEs, B = BS slots,
  * MW = ceil(B/32), F = 2B+1 (central) or 4B+1 (multi-agent)):
