@@ -66,9 +66,12 @@ class ClockSampler(threading.Thread):
     BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
     NOTE = {"sw_power_cap": 0x4}
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True):
         super().__init__(daemon=True)
         self.samples, self.reasons, self.stop_flag, self.ok = [], set(), False, False
+        self.err = "sampled on rank 0 only"
+        if not enabled:
+            return
         try:
             import pynvml
 
@@ -94,7 +97,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         while self.ok and not self.stop_flag:
             self.sample()
-            time.sleep(0.002)
+            time.sleep(0.02)  # 50 Hz: NVML takes a driver lock that graph launches also need
 
     def result(self):
         if not self.ok or not self.samples:
@@ -116,6 +119,40 @@ def ncu_traffic(workload):
     if os.path.exists(path):
         return json.load(open(path)).get(workload)
     return None
+
+
+def workload_shape(workload):
+    fork = workload == "mobile-custom-v0"
+    if fork:
+        size, handler = "mobile-custom", "fork"
+    else:
+        size, handler = workload.rsplit("-", 2)[0], workload.split("-")[2]
+    B, U = SIZES[size]
+    return fork, handler, B, U
+
+
+def rotation(workload, E):
+    """(bytes-per-env-step dict, R, footprint of one batch): the bench rotates over R independent env
+    batches so that a step's inputs and outputs are not L2-resident."""
+    fork, handler, B, U = workload_shape(workload)
+    bpe = bytes_per_env_step_fork(U, B) if fork else bytes_per_env_step(U, B, handler)
+    footprint = E * bpe["layout"]
+    R = max(2, -(-int(2.2 * 126e6) // footprint))
+    return bpe, R, footprint
+
+
+def make_config(args):
+    """`config` of the JSON line: identical for both arms (the reference arm times the same workload
+    on the host cores)."""
+    fork, handler, B, U = workload_shape(args.workload)
+    _, R, footprint = rotation(args.workload, args.envs)
+    return {
+        "workload": args.workload, "envs_per_gpu": args.envs, "bs": B, "ues": U,
+        "actions": "none (FORK step)" if fork else "uniform int32 in [0,B], resident in HBM",
+        "autoreset": True, "ep_time": 20,
+        "l2": f"rotating {R} independent env batches, {R * footprint / 1e6:.0f} MB > 126 MB L2",
+        "launch": "stream launches" if args.no_graph else "CUDA graph replay",
+    }
 
 
 def run_reference(args, rank, world):
@@ -141,15 +178,14 @@ def run_reference(args, rank, world):
     # for transparency only (`value` stays the reference's own speed class, scalar Python): the same
     # arithmetic as a compiled C + OpenMP restatement on the same cores
     compiled = cpu_baseline.run_compiled(workload, 2.0)
-    B, U = SIZES[workload.rsplit("-", 2)[0]]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "envs_per_gpu": args.envs, "bs": B, "ues": U,
-                   "note": "each step = every host core stepping its own env for a bounded time"},
+        "config": make_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
-                         "sample": vals[-1]["sample"], "single_core": vals[-1]["single_core"], "compiled": compiled},
+                         "sample": vals[-1]["sample"] + "; each step = every host core stepping its own env for a "
+                                   "bounded time", "single_core": vals[-1]["single_core"], "compiled": compiled},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -168,6 +204,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--preheat-seconds", type=float, default=1.0)
+    ap.add_argument("--repeats", type=int, default=0,
+                    help="times the K-step block is timed (median reported); 0 = about 2000 / K, at most 200")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -208,17 +246,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    fork = args.workload == "mobile-custom-v0"
-    if fork:
-        size, handler = "mobile-custom", "fork"
-    else:
-        size, handler = args.workload.rsplit("-", 2)[0], args.workload.split("-")[2]
-    B, U = SIZES[size]
+    fork, handler, B, U = workload_shape(args.workload)
     E = args.envs
-    bpe = bytes_per_env_step_fork(U, B) if fork else bytes_per_env_step(U, B, handler)
     # rotate over R independent batches so that each step's inputs/outputs are not L2-resident
-    footprint = E * bpe["layout"]
-    R = max(2, -(-int(2.2 * 126e6) // footprint))
+    bpe, R, footprint = rotation(args.workload, E)
     envs = []
     for r in range(R):
         env = mbe.make(args.workload, num_envs=E, device=str(dev), autoreset=True,
@@ -269,20 +300,36 @@ def main():
         while time.perf_counter() < t_end:
             run_steps(chunk)
             torch.cuda.synchronize()
-        run_steps(max(args.warmup, 3))
+        # warm-up: at least W steps, issued as exactly the K-step sequence the timed region will issue,
+        # so that every CUDA graph replayed under the clock (the full-chunk graph and the remainder
+        # graph) has been launched -- and so uploaded to the device -- before
+        for _ in range(max(2, -(-max(args.warmup, 3) // args.steps))):
+            run_steps(args.steps)
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank)
+        # A short K would make the timed region a few hundred microseconds: the K-step block is then
+        # timed `repeats` times (each bracketed by barrier + synchronize, max over ranks per block) and
+        # the median block is reported.  K x repeats ~ 2,000 steps whatever K is.
+        repeats = max(1, min(200, 2000 // max(args.steps, 1))) if args.repeats <= 0 else args.repeats
+        sampler = ClockSampler(local_rank, enabled=(rank == 0))
         if sampler.ok:
             sampler.sample()
         sampler.start()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        run_steps(args.steps)
-        ev1.record(stream)
-        torch.cuda.synchronize()
+        gate_cycles = int(os.environ.get("MBE_BENCH_GATE_CYCLES", "400000"))  # ~0.2 ms spin kernel
+        pairs = []
+        for _ in range(repeats):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # gate: a spin kernel runs while the host enqueues the event and the graph launches, so the
+            # launch latency of the first graph is not inside the timed region
+            if gate_cycles > 0:
+                torch.cuda._sleep(gate_cycles)
+            ev0.record(stream)
+            run_steps(args.steps)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            pairs.append((ev0, ev1))
         sampler.stop_flag = True
         sampler.join()
         if sampler.ok:
@@ -290,7 +337,11 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1)
+        block_ms = torch.tensor([a_.elapsed_time(b_) for a_, b_ in pairs], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(block_ms, op=dist.ReduceOp.MAX)  # every block: max over ranks
+        block_ms = sorted(float(v) for v in block_ms)
+        ms = statistics.median(block_ms)
         gpu_launches = args.steps  # one step_kernel launch per step (graph nodes included)
 
         # ---- secondary: two env groups in flight (two streams, each its own dependent chain) ----
@@ -407,11 +458,11 @@ def main():
             torch.cuda.synchronize()
             e2e_lite = (time.perf_counter() - t0, rew_h.numel() * 4 + E)
 
-    times = torch.tensor([ms, e2e_s * 1e3, (e2e_lite[0] if e2e_lite else 0.0) * 1e3, two[0] if two else 0.0,
+    times = torch.tensor([0.0, e2e_s * 1e3, (e2e_lite[0] if e2e_lite else 0.0) * 1e3, two[0] if two else 0.0,
                           fused[0] if fused else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, lite_ms, two_ms, fused_ms = (float(t) for t in times)
+    _, e2e_ms, lite_ms, two_ms, fused_ms = (float(t) for t in times)
     if rank == 0:
         peak, peak_src = measured_peak()
         per_launch_s = ms * 1e-3 / args.steps
@@ -421,13 +472,12 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": args.workload, "envs_per_gpu": E, "bs": B, "ues": U,
-                "actions": "none (FORK step)" if fork else "uniform int32 in [0,B], resident in HBM",
-                "autoreset": True, "ep_time": 20,
-                "l2": f"rotating {R} independent env batches, {R * footprint / 1e6:.0f} MB > 126 MB L2",
-                "launch": "CUDA graph replay" if graph is not None else "stream launches",
-            },
+            "config": make_config(args),
+            "repeats": repeats,
+            "timing": {"what": f"median of {repeats} timed blocks of K={args.steps} steps, each block bracketed by "
+                               "barrier + synchronize and taken as the max over ranks; CUDA events on the launching "
+                               "stream behind a spin-kernel gate",
+                       "block_ms_min": block_ms[0], "block_ms_median": ms, "block_ms_max": block_ms[-1]},
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.workload),

@@ -13,7 +13,9 @@
  *   - all calls are stream-ordered on the given cudaStream_t (passed as void*), enqueue
  *     only, never synchronise (except the *_host convenience entry, which says so);
  *   - return 0 on success, non-zero on error; mbe_last_error() gives a thread-local text;
- *   - one handle per device; a handle is not thread-safe, different handles are.
+ *   - a handle belongs to the device named in mbe_config.device; every call makes that device current
+ *     for its duration and restores the caller's current device before returning;
+ *   - a handle is not thread-safe, different handles are.
  *
  * Shapes: U <= 32 and B <= 32 run on the warp-segment kernels (an env is a slice of a warp; the
  * scenario shapes have fused compile-time variants: several UEs per thread for 15 x 4, a thread per
@@ -108,7 +110,9 @@ typedef struct mbe_config {
   int32_t reset_rng_episode; /* movement_params.reset_rng_episode (base.py:130-134) */
   int32_t ep_time;     /* min(EP_MAX_TIME, max departure) (base.py:407-409) */
   int32_t move_d2max;  /* largest integer d2 with sqrt(d2) <= velocity (movement.py:54) */
-  int64_t env_offset;  /* global id of local env 0 (multi-GPU sharding; Philox counters use it) */
+  int64_t env_offset;  /* global id of local env 0 (multi-GPU sharding; Philox counters use it). Global env ids are
+                          one 32-bit counter word: 0 <= env_offset and env_offset + num_envs <= 2^32 - 1, else
+                          mbe_create fails (4.29e9 envs across the job) */
   uint64_t seed;       /* movement seed = config seed + 4 (base.py:155-170) */
   double width, height;/* map (base.py:103) */
   double velocity;     /* ue.velocity (base.py:119) */

@@ -507,7 +507,11 @@ class MComCore:
     def load_state_dict(self, sd):
         for k, v in sd.items():
             getattr(self, k).copy_(v)
+        if "bs_xy" in sd:
+            self._bind()  # a shared layout is folded into the kernel parameters at bind time
         self._needs_reset = False
+        if self.plan.mode == _lib.MODE_GYM:
+            self.observe()  # obs is derived state: recompute it from the loaded positions / connections
 
     def close(self):
         if getattr(self, "_handle", None) and self._handle.value:

@@ -43,6 +43,8 @@ class EnvView:
                     self.bs2ue_dataRates[(stations[b], users[u])] = rate[u]
         else:
             for u, mask in enumerate(env.conn[e].cpu().tolist()):
+                if isinstance(mask, list):  # B > 32: [E,U,MW] words, word i holds BS 32i..32i+31
+                    mask = sum((w & 0xFFFFFFFF) << (32 * i) for i, w in enumerate(mask))
                 for b in range(nbs):
                     if (mask >> b) & 1:
                         self.bs2ue_connections[stations[b]].add(users[u])

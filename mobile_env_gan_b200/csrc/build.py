@@ -1,6 +1,7 @@
 """Builds libmbe.so in-tree with nvcc for sm_100a (the only target)."""
 from __future__ import annotations
 
+import glob
 import os
 import shutil
 import subprocess
@@ -9,7 +10,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libmbe.so")
 SOURCES = ["mbe.cu"]
-DEPS = ["mbe.cu", "mbe_step.cuh", "mbe_step_spec.cuh", "mbe_device.cuh", os.path.join("..", "..", "include", "mbe.h")]
+
+
+def deps():
+    """Every file the library is compiled from: all .cu / .cuh here plus the public header."""
+    files = glob.glob(os.path.join(HERE, "*.cu")) + glob.glob(os.path.join(HERE, "*.cuh"))
+    return sorted(files) + [os.path.join(HERE, "..", "..", "include", "mbe.h")]
 
 
 def nvcc_path() -> str:
@@ -23,7 +29,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(HERE, d)) > t for d in DEPS)
+    return any(os.path.getmtime(d) > t for d in deps())
 
 
 def build(force: bool = False, verbose: bool = False, out: str = None, defines=()) -> str:

@@ -38,6 +38,28 @@ int fail(const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(e_));    \
   } while (0)
 
+// Makes the handle's device current for the duration of a call and restores the caller's device
+// afterwards (a process may drive several devices / handles from one thread).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) {
+      err = cudaSetDevice(device);
+      switched = err == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+#define MBE_ON_DEVICE(dev)                                                                          \
+  DeviceGuard guard_(dev);                                                                          \
+  if (guard_.err != cudaSuccess) return fail("cudaSetDevice(%d): %s", dev, cudaGetErrorString(guard_.err))
+
 }  // namespace
 
 struct mbe_env {
@@ -172,7 +194,9 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     if (cfg->classes[c].d2max >= 0 && !cfg->classes[c].rate_lut)
       return fail("mbe_create: class %d has no rate_lut", c);
 
-  MBE_CUDA(cudaSetDevice(cfg->device));
+  if (cfg->env_offset < 0 || cfg->env_offset + (int64_t)cfg->num_envs > (int64_t)0xffffffffll)
+    return fail("mbe_create: env_offset + num_envs must stay below 2^32 (global env ids are 32-bit Philox counter words)");
+  MBE_ON_DEVICE(cfg->device);
   mbe_env* env = new (std::nothrow) mbe_env();
   if (!env) return fail("mbe_create: out of host memory");
   env->cfg = *cfg;
@@ -415,6 +439,7 @@ void mbe_destroy(mbe_env* env) {
 
 int mbe_bind(mbe_env* env, const mbe_buffers* b) {
   if (!env || !b) return fail("mbe_bind: null argument");
+  MBE_ON_DEVICE(env->cfg.device);
   const bool gym = env->cfg.mode == MBE_MODE_GYM;
   if (!b->pos || !b->wp || !b->t || !b->episode || !b->bs_xy || !b->utility || !b->done)
     return fail("mbe_bind: pos, wp, t, episode, bs_xy, utility and done are required");
@@ -509,6 +534,7 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
                   int window_count = 0) {
   if (!env) return fail("null handle");
   if (!env->bound) return fail("mbe_bind has not been called");
+  MBE_ON_DEVICE(env->cfg.device);
   mbe::StepArgs a = env->args;
   a.op = op;
   a.phases = phases;
@@ -532,7 +558,9 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
     env->launches += 1;
     return 0;
   }
-  if (env->tpe && env->tpe_bound_ok && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr) {
+  // (a window that is not a whole number of 32-env warps falls through to the warp-segment kernels,
+  // which handle ragged tails)
+  if (env->tpe && env->tpe_bound_ok && a.E % 32 == 0 && op == mbe::OP_STEP && phases == MBE_PHASE_ALL && !a.dbg_snr) {
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(a.E / 32);
     lc.blockDim = dim3(32);
@@ -621,6 +649,7 @@ int mbe_observe(mbe_env* env, void* stream) {
 int mbe_channel(mbe_env* env, float* out_snr, uint32_t* out_elig, void* stream) {
   if (!env) return fail("null handle");
   if (!env->bound) return fail("mbe_bind has not been called");
+  MBE_ON_DEVICE(env->cfg.device);
   const mbe::StepArgs& a = env->args;
   if (out_elig && a.B > 32) return fail("mbe_channel: the connectable bitmask output needs num_bs <= 32");
   const size_t total = (size_t)a.E * a.U;
@@ -636,6 +665,7 @@ int mbe_accumulate_qoe(mbe_env* env, float* acc, float threshold, void* stream) 
   if (!env || !acc) return fail("mbe_accumulate_qoe: null argument");
   if (!env->bound) return fail("mbe_bind has not been called");
   if ((uintptr_t)acc & 15) return fail("mbe_accumulate_qoe: acc must be 16-byte aligned");
+  MBE_ON_DEVICE(env->cfg.device);
   const mbe::StepArgs& a = env->args;
   const int per_blk = mbe::kThreads / 32;
   mbe::qoe_accumulate_kernel<<<(a.E + per_blk - 1) / per_blk, mbe::kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -651,6 +681,7 @@ int mbe_rollout(mbe_env* env, int steps, float* qoe_acc, float threshold, const 
   if (env->cfg.mode != MBE_MODE_FORK) return fail("mbe_rollout: FORK mode only (a GYM step needs fresh actions)");
   if (steps <= 0) return fail("mbe_rollout: steps must be positive");
   if ((uintptr_t)qoe_acc & 15) return fail("mbe_rollout: qoe_acc must be 16-byte aligned");
+  MBE_ON_DEVICE(env->cfg.device);
   const mbe_rollout_out none = {};
   const mbe_rollout_out& o = out ? *out : none;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -708,6 +739,7 @@ int mbe_step_host(mbe_env* env, const int32_t* actions_host, float* obs_host, fl
                   uint8_t* done_host, void* stream) {
   if (!env) return fail("null handle");
   if (!env->bound) return fail("mbe_bind has not been called");
+  MBE_ON_DEVICE(env->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const mbe::StepArgs& a = env->args;
   const bool gym = env->cfg.mode == MBE_MODE_GYM, ma = env->cfg.handler == MBE_HANDLER_MA;

@@ -13,23 +13,31 @@ import numpy as np
 
 from oracle import mbe_oracle as orc
 
+_MEDIUM = [(50, 50), (150, 50), (50, 150), (150, 150)]
+_LARGE = [(20 + 45 * (i % 4) + (22 if (i // 4) % 2 else 0), 25 + 50 * (i // 4)) for i in range(13)]
+_SYNTH = [((i * 7919 + 13) % 800, (i * 104729 + 71) % 800) for i in range(64)]
+_SYNTH_P = {"width": 800.0, "height": 800.0, "scheduler": "proportional_fair"}
 WORKLOADS = {
-    # name: (bs_xy, num_ues, mode, handler, velocity)
-    "mobile-small-central-v0": ([(110, 130), (65, 80), (120, 30)], 5, "gym", "central", 1.5),
-    "mobile-medium-central-v0": ([(50, 50), (150, 50), (50, 150), (150, 150)], 15, "gym", "central", 1.5),
-    "mobile-medium-ma-v0": ([(50, 50), (150, 50), (50, 150), (150, 150)], 15, "gym", "ma", 1.5),
-    "mobile-large-central-v0": (
-        [(20 + 45 * (i % 4) + (22 if (i // 4) % 2 else 0), 25 + 50 * (i // 4)) for i in range(13)],
-        30, "gym", "central", 1.5),
+    # name: (bs_xy, num_ues, mode, handler, velocity, Params overrides) -- the layouts of
+    # mobile_env_gan_b200/scenarios/*.py
+    "mobile-small-central-v0": ([(110, 130), (65, 80), (120, 30)], 5, "gym", "central", 1.5, {}),
+    "mobile-small-ma-v0": ([(110, 130), (65, 80), (120, 30)], 5, "gym", "ma", 1.5, {}),
+    "mobile-medium-central-v0": (_MEDIUM, 15, "gym", "central", 1.5, {}),
+    "mobile-medium-ma-v0": (_MEDIUM, 15, "gym", "ma", 1.5, {}),
+    "mobile-large-central-v0": (_LARGE, 30, "gym", "central", 1.5, {}),
+    "mobile-large-ma-v0": (_LARGE, 30, "gym", "ma", 1.5, {}),
+    # BASELINE.json configs[4]: 64 BS x 512 UE, ProportionalFair, 800 x 800 map
+    "mobile-synthetic-central-v0": (_SYNTH, 512, "gym", "central", 1.5, _SYNTH_P),
+    "mobile-synthetic-ma-v0": (_SYNTH, 512, "gym", "ma", 1.5, _SYNTH_P),
     # the fork's own scenario (custom.py): 7 UEs at velocity 10, 5..10 random BSs per episode, FORK step
-    "mobile-custom-v0": (None, 7, "fork", "central", 10),
+    "mobile-custom-v0": (None, 7, "fork", "central", 10, {}),
 }
 
 
 def _worker(args):
     workload, seconds, seed = args
-    bs, U, mode, handler, vel = WORKLOADS[workload]
-    p = orc.Params(velocity=vel)
+    bs, U, mode, handler, vel, over = WORKLOADS[workload]
+    p = orc.Params(velocity=vel, **over)
     rng = np.random.default_rng(seed)
     random_layout = bs is None
     env = orc.ScalarEnv(p, bs or [(0, 0)], U,
@@ -37,7 +45,7 @@ def _worker(args):
 
     def fresh():
         if random_layout:  # generate_base_stations (custom.py:68-77)
-            env.bs_xy = [(int(rng.uniform(0, 200)), int(rng.uniform(0, 200))) for _ in range(int(rng.integers(5, 11)))]
+            env.bs_xy = [(int(rng.uniform(0, p.width)), int(rng.uniform(0, p.height))) for _ in range(int(rng.integers(5, 11)))]
         env.reset([(int(rng.uniform(0, p.width)), int(rng.uniform(0, p.height))) for _ in range(U)])
 
     fresh()
@@ -52,7 +60,7 @@ def _worker(args):
         steps += 1
         if done:
             fresh()
-        if steps % 8 == 0 and time.perf_counter() - t0 >= seconds:
+        if (steps % 8 == 0 or U > 64) and time.perf_counter() - t0 >= seconds:
             break
     return steps, time.perf_counter() - t0
 
@@ -107,9 +115,10 @@ def _compiled_worker(args):
     workload, seconds, envs = args
     from oracle.c_oracle import CEnvBatch
 
-    bs, U, mode, handler, vel = WORKLOADS[workload]
-    p = orc.Params(velocity=vel)
+    bs, U, mode, handler, vel, over = WORKLOADS[workload]
+    p = orc.Params(velocity=vel, **over)
     rng = np.random.default_rng(7)
+    envs = max(64, min(envs, (1 << 22) // (U * len(bs or [0] * 10))))  # bound the wide shapes' memory and time
     E = envs
     if bs is None:  # the fork's scenario: 5..10 random BSs per env (custom.py:68-77)
         layout = rng.integers(0, 200, size=(E, 10, 2)).astype(np.int32)
@@ -136,7 +145,7 @@ def _compiled_worker(args):
             fresh()
         if time.perf_counter() - t0 >= seconds:
             break
-    return calls * E, time.perf_counter() - t0
+    return calls * E, time.perf_counter() - t0, E
 
 
 def run_compiled(workload: str, seconds: float = 2.0, envs: int = 8192):
@@ -156,7 +165,7 @@ def run_compiled(workload: str, seconds: float = 2.0, envs: int = 8192):
                              cwd=root, capture_output=True, text=True, timeout=seconds + 120)
         if res.returncode != 0:
             raise RuntimeError(res.stderr.strip().splitlines()[-1] if res.stderr.strip() else f"exit {res.returncode}")
-        steps, wall = json.loads(res.stdout.strip().splitlines()[-1])
+        steps, wall, envs = json.loads(res.stdout.strip().splitlines()[-1])
     except Exception as exc:  # noqa: BLE001
         return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
     return {

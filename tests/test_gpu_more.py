@@ -346,3 +346,90 @@ def test_step_kernel_name_reports_the_dispatched_family():
     assert MComCustom(config={"num_envs": 40}).step_kernel_name == "step_spec_kernel"  # E % 32 != 0
     generic = mbe.make("mobile-medium-central-v0", num_envs=64, config={"generic_kernel": True})
     assert generic.step_kernel_name == "step_kernel"
+
+
+def test_fork_step_window_ragged_tail_and_tiny_window():
+    """A window that is not a whole number of 32-env warps (or holds fewer than 32 envs) must still
+    step exactly its envs: the thread-per-env FORK kernel only takes whole warps, so such windows
+    fall through to the warp-segment kernel (same results bit for bit)."""
+    from mobile_env_gan_b200.scenarios.custom import MComCustom
+
+    E = 4096
+    a = MComCustom(config={"num_envs": E, "autoreset": True})
+    b = MComCustom(config={"num_envs": E, "autoreset": True})
+    a.reset(), b.reset()
+    names = ("pos", "wp", "t", "episode", "assoc", "rate", "utility_scaled", "metrics", "done", "bs_xy", "nbs")
+    for s in range(23):
+        before = {n: getattr(a, n).clone() for n in names}
+        b.step(0, s)
+        a.step_window(0, 17)          # fewer envs than one warp of the thread-per-env kernel
+        a.step_window(1024, 1000)     # ragged tail: 31 warps + 8 envs
+        a.step_window(2048, 2048)     # whole warps: thread-per-env kernel
+        torch.cuda.synchronize()
+        stepped = torch.zeros(E, dtype=torch.bool, device="cuda")
+        stepped[:17] = True
+        stepped[1024:2024] = True
+        stepped[2048:] = True
+        for n in names:
+            got, want, old = getattr(a, n), getattr(b, n), before[n]
+            assert torch.equal(got[stepped], want[stepped]), (n, s)
+            assert torch.equal(got[~stepped], old[~stepped]), (n, s)
+        # bring the untouched envs level with b for the next step
+        for n in names:
+            getattr(a, n).copy_(getattr(b, n))
+
+
+def test_load_state_dict_rebinds_a_shared_layout_and_recomputes_obs():
+    import mobile_env_gan_b200 as mbe
+
+    env = mbe.make("mobile-small-central-v0", num_envs=256)
+    ref = mbe.make("mobile-small-central-v0", num_envs=256)
+    env.reset(), ref.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    acts = [torch.randint(0, 4, (256, 5), generator=g, device="cuda", dtype=torch.int32) for _ in range(12)]
+    for a in acts[:4]:
+        env.step(a), ref.step(a)
+    snap = env.state_dict()
+    obs_at_snap = env.obs.clone()
+    env.set_station_positions(torch.tensor([[10, 10], [190, 190], [100, 100]]))  # another layout
+    for a in acts[4:8]:
+        env.step(a)
+    env.load_state_dict(snap)  # back to the original layout: must re-fold it into the kernel parameters
+    assert torch.equal(env.obs, obs_at_snap)
+    for a in acts[4:]:
+        o1, r1, *_ = env.step(a)
+        o2, r2, *_ = ref.step(a)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2)
+        assert torch.equal(env.conn, ref.conn) and torch.equal(env.rate, ref.rate)
+
+
+def test_env_view_wide_shape_combines_mask_words():
+    import mobile_env_gan_b200 as mbe
+
+    env = mbe.make("mobile-synthetic-central-v0", num_envs=2)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for _ in range(3):
+        env.step(torch.randint(0, 65, (2, 512), generator=g, device="cuda", dtype=torch.int32))
+    v = env.view(1)
+    conn = env.conn[1].cpu().numpy().astype(np.int64) & 0xFFFFFFFF  # [U, 2]
+    want = int(sum(bin(int(w)).count("1") for w in conn.reshape(-1)))
+    assert sum(len(ues) for ues in v.bs2ue_connections.values()) == want
+    hi = [bs.bs_id for bs, ues in v.bs2ue_connections.items() if ues and bs.bs_id >= 32]
+    assert (conn[:, 1] != 0).any() == bool(hi)
+
+
+def test_handle_on_another_device_does_not_change_the_current_device():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import mobile_env_gan_b200 as mbe
+
+    torch.cuda.set_device(0)
+    env = mbe.make("mobile-small-central-v0", num_envs=64, device="cuda:1")
+    assert torch.cuda.current_device() == 0
+    env.reset()
+    with torch.cuda.device(1):
+        acts = torch.zeros(64, 5, dtype=torch.int32, device="cuda:1")
+    env.step(acts)
+    torch.cuda.synchronize(1)
+    assert torch.cuda.current_device() == 0
