@@ -52,13 +52,14 @@
 extern "C" {
 #endif
 
-#define MBE_ABI_VERSION 1
+#define MBE_ABI_VERSION 2
 
 enum { MBE_MODE_FORK = 0, MBE_MODE_GYM = 1 };
 enum { MBE_HANDLER_CENTRAL = 0, MBE_HANDLER_MA = 1 };
 enum { MBE_SCHED_RESOURCE_FAIR = 0, MBE_SCHED_PROPORTIONAL_FAIR = 1, MBE_SCHED_RATE_FAIR = 2 };
 enum { MBE_BS_SHARED = 0, MBE_BS_PER_ENV = 1 };
-enum { MBE_MAX_CLASSES = 8 };
+enum { MBE_MAX_CLASSES = 16 };   /* link classes = BS classes x UE classes */
+enum { MBE_MAX_UE_CLASSES = 8 };
 /* mbe_config.flags */
 enum {
   MBE_FLAG_GENERIC_KERNEL = 1,    /* never use the shape-specialised fused kernels */
@@ -78,21 +79,35 @@ enum {
   MBE_PHASE_ALL = 15
 };
 
-/* One class of base station (all BSs that share bw/freq/tx/height; UEs are homogeneous).
- * The constants are folded on the host in FP64 from OkumuraHata.power_loss
- * (channels.py:132-146) and Channel.calculateSNR (channels.py:24-27):
- *    log2(snr(d2)) = l0 - k * log2(d2)   for d2 >= 1,   l_zero for d2 == 0 (EPSILON, channels.py:8)
- * d2max is the largest integer squared distance with snr > snr_threshold (base.py:212-214)
- * evaluated with the reference's own FP64 operation order; rate_lut[d2] (HOST pointer,
- * d2max+1 doubles, copied by mbe_create) is Channel.datarate = bw*log2(1+snr) (channels.py:78-83). */
-typedef struct mbe_bs_class {
+/* One LINK class: all (BS, UE) pairs whose BS shares bw/freq/tx/height (entities.py:6-29) and whose UE
+ * shares snr_threshold/noise/height (entities.py:32-57).  Link class of the pair (b, u) =
+ * bs_class[b] * num_ue_classes + ue_class[u].  The tables are folded on the host in FP64 from the
+ * channel's power_loss (channels.py:18-21, 132-146) through Channel.calculateSNR (channels.py:24-27),
+ * evaluated at the integer offsets that realise each squared distance d2 (entities.py:24-26,52-54):
+ *    d2max        largest d2 with snr > snr_threshold (base.py:212-214), -1: never connectable;
+ *    rate_lut     HOST pointer, d2max+1 doubles, copied by mbe_create: Channel.datarate =
+ *                 bw*log2(1+snr) (channels.py:78-83);
+ *    log2(snr(d2)) for the FP32 observation path: l0 - k*log2(d2) for d2 >= 1 and l_zero for
+ *                 d2 == 0 (EPSILON, channels.py:8) when log2snr_lut is NULL, else the table
+ *                 log2snr_lut[d2] (HOST pointer, log2snr_len floats covering every d2 of the map,
+ *                 copied by mbe_create) for losses that are not affine in log-distance. */
+typedef struct mbe_link_class {
   double l0;
   double k;
   double l_zero;
   int32_t d2max; /* -1: never connectable */
-  int32_t reserved;
+  int32_t log2snr_len;
   const double* rate_lut;
-} mbe_bs_class;
+  const float* log2snr_lut;
+} mbe_link_class;
+typedef mbe_link_class mbe_bs_class; /* ABI 1 name */
+
+/* One UE class: the movement parameters of the UEs that share a parameter set (entities.py:32-57) */
+typedef struct mbe_ue_class {
+  double velocity;    /* ue.velocity (base.py:119) */
+  int32_t move_d2max; /* largest integer d2 with sqrt(d2) <= velocity (movement.py:54) */
+  int32_t reserved;
+} mbe_ue_class;
 
 typedef struct mbe_config {
   int32_t abi_version; /* MBE_ABI_VERSION */
@@ -115,12 +130,16 @@ typedef struct mbe_config {
                           mbe_create fails (4.29e9 envs across the job) */
   uint64_t seed;       /* movement seed = config seed + 4 (base.py:155-170) */
   double width, height;/* map (base.py:103) */
-  double velocity;     /* ue.velocity (base.py:119) */
+  double velocity;     /* ue.velocity (base.py:119) of UE class 0 */
   double util_lower, util_upper, util_w1, util_w2, util_w3; /* utilities.py:30-55 */
-  int32_t num_classes; /* 1..MBE_MAX_CLASSES */
+  int32_t num_classes; /* number of BS classes, >= 1; num_classes * max(1, num_ue_classes) <= MBE_MAX_CLASSES */
   int32_t flags;       /* MBE_FLAG_* */
-  mbe_bs_class classes[MBE_MAX_CLASSES];
+  mbe_link_class classes[MBE_MAX_CLASSES]; /* [bs class][ue class], ue class fastest */
   const uint8_t* bs_class; /* HOST [B] class id per BS slot, or NULL = all class 0 */
+  int32_t num_ue_classes;  /* 0 or 1: all UEs alike (velocity / move_d2max above); else 2..MBE_MAX_UE_CLASSES */
+  int32_t reserved2;
+  const uint8_t* ue_class; /* HOST [U] class id per UE (required when num_ue_classes > 1) */
+  mbe_ue_class ue_classes[MBE_MAX_UE_CLASSES]; /* used when num_ue_classes > 1 */
 } mbe_config;
 
 typedef struct mbe_buffers {
@@ -153,6 +172,9 @@ typedef struct mbe_env mbe_env;
 int mbe_abi_version(void);
 const char* mbe_build_info(void);
 const char* mbe_last_error(void);
+/* sizeof of the ABI structs as the library was compiled (0 mbe_config, 1 mbe_buffers, 2 mbe_link_class,
+ * 3 mbe_ue_class, 4 mbe_rollout_out; -1 otherwise): lets a binding in another language check its layout */
+int mbe_struct_size(int which);
 
 /* replaces MComCore.__init__ (base.py:32-100): validates, copies the constant tables */
 int mbe_create(const mbe_config* cfg, mbe_env** out);

@@ -10,12 +10,13 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MBE_LIB_PATH") or os.path.join(HERE, "csrc", "libmbe.so")
 
-MBE_ABI_VERSION = 1
+MBE_ABI_VERSION = 2
 MODE_FORK, MODE_GYM = 0, 1
 HANDLER_CENTRAL, HANDLER_MA = 0, 1
 SCHED_RESOURCE_FAIR, SCHED_PROPORTIONAL_FAIR, SCHED_RATE_FAIR = 0, 1, 2
 BS_SHARED, BS_PER_ENV = 0, 1
-MAX_CLASSES = 8
+MAX_CLASSES = 16
+MAX_UE_CLASSES = 8
 FLAG_GENERIC_KERNEL = 1
 FLAG_SHARED_TRAJECTORY = 2
 PHASE_MOVE, PHASE_PRE, PHASE_CLOCK, PHASE_POST, PHASE_ALL = 1, 2, 4, 8, 15
@@ -27,9 +28,14 @@ class BsClass(C.Structure):
         ("k", C.c_double),
         ("l_zero", C.c_double),
         ("d2max", C.c_int32),
-        ("reserved", C.c_int32),
+        ("log2snr_len", C.c_int32),
         ("rate_lut", C.POINTER(C.c_double)),
+        ("log2snr_lut", C.POINTER(C.c_float)),
     ]
+
+
+class UeClass(C.Structure):
+    _fields_ = [("velocity", C.c_double), ("move_d2max", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Config(C.Structure):
@@ -63,6 +69,10 @@ class Config(C.Structure):
         ("flags", C.c_int32),
         ("classes", BsClass * MAX_CLASSES),
         ("bs_class", C.POINTER(C.c_uint8)),
+        ("num_ue_classes", C.c_int32),
+        ("reserved2", C.c_int32),
+        ("ue_class", C.POINTER(C.c_uint8)),
+        ("ue_classes", UeClass * MAX_UE_CLASSES),
     ]
 
 
@@ -103,6 +113,7 @@ SYMBOLS = [
     ("mbe_abi_version", C.c_int, []),
     ("mbe_build_info", C.c_char_p, []),
     ("mbe_last_error", C.c_char_p, []),
+    ("mbe_struct_size", C.c_int, [C.c_int]),
     ("mbe_create", C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     ("mbe_destroy", None, [C.c_void_p]),
     ("mbe_bind", C.c_int, [C.c_void_p, C.POINTER(Buffers)]),
@@ -143,6 +154,10 @@ def load():
         fn.argtypes = args
     if lib.mbe_abi_version() != MBE_ABI_VERSION:
         raise MbeError(f"libmbe ABI {lib.mbe_abi_version()} != binding {MBE_ABI_VERSION}")
+    for which, struct in enumerate((Config, Buffers, BsClass, UeClass, RolloutOut)):
+        if lib.mbe_struct_size(which) != C.sizeof(struct):
+            raise MbeError(f"struct layout mismatch: {struct.__name__} is {C.sizeof(struct)} bytes here, "
+                           f"{lib.mbe_struct_size(which)} in {LIB_PATH}")
     _lib = lib
     return lib
 

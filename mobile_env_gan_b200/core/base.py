@@ -60,9 +60,12 @@ class Plan:
     utility: tuple
     scheduler: int = 0
     shared_trajectory: bool = False
-    classes: List[dict] = field(default_factory=list)
+    classes: List[dict] = field(default_factory=list)  # link classes [bs class][ue class], ue class fastest
     bs_class: Optional[np.ndarray] = None
     bs_xy: Optional[np.ndarray] = None  # shared layout [B,2] int16
+    num_bs_classes: int = 1
+    ue_class: Optional[np.ndarray] = None  # [U] uint8, None = all UEs alike
+    ue_classes: List[dict] = field(default_factory=list)  # per UE class: velocity, move_d2max
 
     @property
     def feature_size(self) -> int:
@@ -142,9 +145,19 @@ class MComCore:
             raise TypeError("channel must derive from Channel")
         if not users:
             raise ValueError("at least one UE is required")
-        ue0 = users[0]
-        if any(ue.radio_key() != ue0.radio_key() for ue in users):
-            raise NotImplementedError("heterogeneous UE parameters are not supported by the kernels")
+        # UE classes: UEs that share velocity / snr_threshold / noise / height (entities.py:32-57)
+        users = sorted(users, key=lambda u: u.ue_id)
+        ue_keys, ue_protos = [], []
+        ue_class = np.zeros(len(users), dtype=np.uint8)
+        for i, ue in enumerate(users):
+            k = ue.radio_key()
+            if k not in ue_keys:
+                ue_keys.append(k)
+                ue_protos.append(ue)
+            ue_class[i] = ue_keys.index(k)
+        if len(ue_keys) > _lib.MAX_UE_CLASSES:
+            raise NotImplementedError(f"more than {_lib.MAX_UE_CLASSES} distinct UE parameter sets")
+        ue0 = ue_protos[0]
         width, height = float(config["width"]), float(config["height"])
         if not (0 < width <= MAX_COORD and 0 < height <= MAX_COORD):
             raise ValueError("map does not fit int16 coordinates")
@@ -154,8 +167,7 @@ class MComCore:
         max_d2 = int(width) ** 2 + int(height) ** 2 + 2
         if bs_random:
             nbs = int(config.get("max_bs") or bs_random[1])
-            proto = BaseStation(0, (0, 0), **config["bs"])
-            classes = [channel.fold(proto, ue0, max_d2)]
+            bs_protos = [BaseStation(0, (0, 0), **config["bs"])]
             bs_class, bs_xy, layout = None, None, _lib.BS_PER_ENV
             bs_random = (int(bs_random[0]), int(bs_random[1]))
         else:
@@ -163,19 +175,31 @@ class MComCore:
                 raise ValueError("stations are required unless config['bs_random'] is set")
             stations = sorted(stations, key=lambda b: b.bs_id)
             nbs = len(stations)
-            keys, classes = [], []
+            keys, bs_protos = [], []
             bs_class = np.zeros(nbs, dtype=np.uint8)
             for i, bs in enumerate(stations):
                 k = bs.radio_key()
                 if k not in keys:
                     keys.append(k)
-                    classes.append(channel.fold(bs, ue0, max_d2))
+                    bs_protos.append(bs)
                 bs_class[i] = keys.index(k)
-            if len(classes) > _lib.MAX_CLASSES:
-                raise NotImplementedError(f"more than {_lib.MAX_CLASSES} distinct BS parameter sets")
             bs_xy = np.array([[int(b.x), int(b.y)] for b in stations], dtype=np.int16)  # entities.py:24-26
             layout, bs_random = _lib.BS_SHARED, (0, 0)
-        mv = movement.device_params(ue0.velocity)
+        if len(bs_protos) * len(ue_protos) > _lib.MAX_CLASSES:
+            raise NotImplementedError(
+                f"{len(bs_protos)} BS parameter sets x {len(ue_protos)} UE parameter sets exceed {_lib.MAX_CLASSES} link classes")
+        # one folded table set per (BS class, UE class) pair; UE classes that differ in velocity only
+        # share the fold of their radio parameters
+        folds = {}
+        classes = []
+        for bs in bs_protos:
+            for ue in ue_protos:
+                key = (bs.radio_key(), ue.radio_key()[1:])
+                if key not in folds:
+                    folds[key] = channel.fold(bs, ue, max_d2)
+                classes.append(folds[key])
+        ue_classes = [movement.device_params(ue.velocity) for ue in ue_protos]
+        mv = ue_classes[0]
         w1, w2, w3 = utility.coeffs
         ep_time = int(min(config["EP_MAX_TIME"], arrival.ep_time))  # base.py:407-409 with NoDeparture
         shared = config.get("shared_trajectory", False)
@@ -189,7 +213,8 @@ class MComCore:
             width=width, height=height, velocity=mv["velocity"], move_d2max=mv["move_d2max"],
             utility=(float(utility.lower), float(utility.upper), float(w1), float(w2), float(w3)),
             scheduler=int(scheduler.kernel_id), shared_trajectory=bool(shared), classes=classes, bs_class=bs_class,
-            bs_xy=bs_xy,
+            bs_xy=bs_xy, num_bs_classes=len(bs_protos), ue_class=ue_class if len(ue_protos) > 1 else None,
+            ue_classes=ue_classes,
         )
 
     @staticmethod
@@ -287,7 +312,7 @@ class MComCore:
         cfg.seed = p.seed & 0xFFFFFFFFFFFFFFFF
         cfg.width, cfg.height, cfg.velocity = p.width, p.height, p.velocity
         cfg.util_lower, cfg.util_upper, cfg.util_w1, cfg.util_w2, cfg.util_w3 = p.utility
-        cfg.num_classes = len(p.classes)
+        cfg.num_classes = p.num_bs_classes
         cfg.flags = (_lib.FLAG_GENERIC_KERNEL if self.config.get("generic_kernel") else 0) | (
             _lib.FLAG_SHARED_TRAJECTORY if p.shared_trajectory else 0)
         for i, c in enumerate(p.classes):
@@ -296,6 +321,17 @@ class MComCore:
             cfg.classes[i].l0, cfg.classes[i].k, cfg.classes[i].l_zero = c["l0"], c["k"], c["l_zero"]
             cfg.classes[i].d2max = c["d2max"]
             cfg.classes[i].rate_lut = lut.ctypes.data_as(C.POINTER(C.c_double)) if len(lut) else None
+            if c.get("log2snr_lut") is not None:
+                ltab = np.ascontiguousarray(c["log2snr_lut"], dtype=np.float32)
+                self._keepalive.append(ltab)
+                cfg.classes[i].log2snr_lut = ltab.ctypes.data_as(C.POINTER(C.c_float))
+                cfg.classes[i].log2snr_len = len(ltab)
+        if p.ue_class is not None:
+            self._keepalive.append(p.ue_class)
+            cfg.num_ue_classes = len(p.ue_classes)
+            cfg.ue_class = p.ue_class.ctypes.data_as(C.POINTER(C.c_uint8))
+            for i, uc in enumerate(p.ue_classes):
+                cfg.ue_classes[i].velocity, cfg.ue_classes[i].move_d2max = uc["velocity"], uc["move_d2max"]
         if p.bs_class is not None:
             self._keepalive.append(p.bs_class)
             cfg.bs_class = p.bs_class.ctypes.data_as(C.POINTER(C.c_uint8))

@@ -67,8 +67,9 @@ struct mbe_env {
   mbe_buffers bufs;
   bool bound = false;
   mbe::StepArgs args;
-  std::vector<double*> luts;
+  std::vector<void*> luts;  // device tables owned by the handle
   uint8_t* d_bs_class = nullptr;
+  uint8_t* d_ue_class = nullptr;
   size_t smem = 0;
   int grid = 0;
   int64_t launches = 0;
@@ -158,7 +159,20 @@ extern "C" {
 int mbe_abi_version(void) { return MBE_ABI_VERSION; }
 
 const char* mbe_build_info(void) {
-  return "libmbe abi " "1" " | sm_100a | built " __DATE__ " " __TIME__;
+#define MBE_STR2(x) #x
+#define MBE_STR(x) MBE_STR2(x)
+  return "libmbe abi " MBE_STR(MBE_ABI_VERSION) " | sm_100a | built " __DATE__ " " __TIME__;
+}
+
+int mbe_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(mbe_config);
+    case 1: return (int)sizeof(mbe_buffers);
+    case 2: return (int)sizeof(mbe_link_class);
+    case 3: return (int)sizeof(mbe_ue_class);
+    case 4: return (int)sizeof(mbe_rollout_out);
+    default: return -1;
+  }
 }
 
 const char* mbe_last_error(void) { return g_err.c_str(); }
@@ -179,8 +193,13 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   if (cfg->scheduler != MBE_SCHED_RESOURCE_FAIR && cfg->scheduler != MBE_SCHED_PROPORTIONAL_FAIR &&
       cfg->scheduler != MBE_SCHED_RATE_FAIR)
     return fail("mbe_create: scheduler %d not available", cfg->scheduler);
-  if (cfg->num_classes < 1 || cfg->num_classes > MBE_MAX_CLASSES)
-    return fail("mbe_create: num_classes=%d out of range", cfg->num_classes);
+  const int nuc = cfg->num_ue_classes > 1 ? cfg->num_ue_classes : 1;
+  if (nuc > MBE_MAX_UE_CLASSES) return fail("mbe_create: num_ue_classes=%d out of range", cfg->num_ue_classes);
+  if (nuc > 1 && !cfg->ue_class) return fail("mbe_create: num_ue_classes > 1 needs ue_class");
+  if (cfg->num_classes < 1 || cfg->num_classes * nuc > MBE_MAX_CLASSES)
+    return fail("mbe_create: %d BS classes x %d UE classes exceed %d link classes", cfg->num_classes, nuc,
+                MBE_MAX_CLASSES);
+  const int nlink = cfg->num_classes * nuc;
   if (!(cfg->width > 0 && cfg->width <= 32767 && cfg->height > 0 && cfg->height <= 32767))
     return fail("mbe_create: map %gx%g does not fit int16 coordinates", cfg->width, cfg->height);
   if (cfg->ep_time <= 0) return fail("mbe_create: ep_time must be > 0");
@@ -190,9 +209,15 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     return fail("mbe_create: random BS layouts need bs_layout=PER_ENV and 1 <= min <= max <= num_bs");
   if (!(cfg->util_upper > cfg->util_lower) || !(cfg->util_w3 > 0) || cfg->util_w3 == 1.0)
     return fail("mbe_create: bad utility parameters");
-  for (int c = 0; c < cfg->num_classes; ++c)
+  for (int c = 0; c < nlink; ++c) {
     if (cfg->classes[c].d2max >= 0 && !cfg->classes[c].rate_lut)
-      return fail("mbe_create: class %d has no rate_lut", c);
+      return fail("mbe_create: link class %d has no rate_lut", c);
+    if (cfg->classes[c].log2snr_lut && cfg->classes[c].log2snr_len <= 0)
+      return fail("mbe_create: link class %d: log2snr_lut needs log2snr_len > 0", c);
+  }
+  if (nuc > 1)
+    for (int u = 0; u < cfg->num_ues; ++u)
+      if (cfg->ue_class[u] >= nuc) return fail("mbe_create: ue_class[%d]=%d >= num_ue_classes", u, cfg->ue_class[u]);
 
   if (cfg->env_offset < 0 || cfg->env_offset + (int64_t)cfg->num_envs > (int64_t)0xffffffffll)
     return fail("mbe_create: env_offset + num_envs must stay below 2^32 (global env ids are 32-bit Philox counter words)");
@@ -224,14 +249,18 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   a.seed_hi = (unsigned)(cfg->seed >> 32);
   a.width = cfg->width;
   a.height = cfg->height;
-  a.velocity = cfg->velocity;
   a.wh_int = (cfg->width == std::floor(cfg->width) && cfg->height == std::floor(cfg->height)) ? 1 : 0;
   a.wh_int_w = (int)cfg->width;
   a.wh_int_h = (int)cfg->height;
-  a.velocity_f = (float)cfg->velocity;
-  a.tie_eps = (float)(cfg->velocity * 1e-6 + 1e-6);
-  {  // is an axis-aligned step exactly +-velocity in the reference's FP64 chain (movement.py:58-59)?
-    volatile double v = cfg->velocity;
+  for (int c = 0; c < nuc; ++c) {
+    const double vel = nuc > 1 ? cfg->ue_classes[c].velocity : cfg->velocity;
+    mbe::MoveDev& m = a.mv[c];
+    m.velocity = vel;
+    m.velocity_f = (float)vel;
+    m.tie_eps = (float)(vel * 1e-6 + 1e-6);
+    m.move_d2max = nuc > 1 ? cfg->ue_classes[c].move_d2max : cfg->move_d2max;
+    // is an axis-aligned step exactly +-velocity in the reference's FP64 chain (movement.py:58-59)?
+    volatile double v = vel;
     int ok = 1;
     const int dmax = (int)std::max(cfg->width, cfg->height) + 1;
     for (int d = 1; d <= dmax && ok; ++d) {
@@ -239,9 +268,8 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
       volatile double q = prod / (double)d;
       if (q != v) ok = 0;
     }
-    a.axis_exact = ok;
+    m.axis_exact = ok;
   }
-  a.move_d2max = cfg->move_d2max;
   a.util_c = (float)(cfg->util_w1 * std::log(2.0) / std::log(cfg->util_w3));
   a.util_w2 = (float)cfg->util_w2;
   a.util_lo = (float)cfg->util_lower;
@@ -249,8 +277,10 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   a.util_scale = (float)(2.0 / (cfg->util_upper - cfg->util_lower));
   a.inv_U = 1.0f / (float)a.U;
   a.n_classes = cfg->num_classes;
-  for (int c = 0; c < cfg->num_classes; ++c) {
-    const mbe_bs_class& h = cfg->classes[c];
+  a.n_ue_classes = nuc;
+  bool any_ltab = false;
+  for (int c = 0; c < nlink; ++c) {
+    const mbe_link_class& h = cfg->classes[c];
     mbe::ClassDev& d = a.cls[c];
     d.l0_hi = (float)h.l0;
     d.l0_lo = (float)(h.l0 - (double)d.l0_hi);
@@ -261,6 +291,22 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     d.stride = h.d2max + 1;
     d.lutn = nullptr;
     d.lut0 = nullptr;
+    d.ltab = nullptr;
+    d.ltab_len = 0;
+    if (h.log2snr_lut) {  // log2 snr per d2 (loss not affine in log-distance)
+      float* pt = nullptr;
+      size_t bytes = (size_t)h.log2snr_len * sizeof(float);
+      cudaError_t e0 = cudaMalloc(&pt, bytes);
+      if (e0 == cudaSuccess) e0 = cudaMemcpy(pt, h.log2snr_lut, bytes, cudaMemcpyHostToDevice);
+      if (e0 != cudaSuccess) {
+        mbe_destroy(env);
+        return fail("mbe_create: log2snr_lut upload failed: %s", cudaGetErrorString(e0));
+      }
+      env->luts.push_back(pt);
+      d.ltab = pt;
+      d.ltab_len = h.log2snr_len;
+      any_ltab = true;
+    }
     if (h.d2max >= 0) {  // the raw table, for the block-per-env kernel
       double* p0 = nullptr;
       size_t bytes0 = (size_t)d.stride * sizeof(double);
@@ -311,9 +357,18 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     }
     a.bs_class = env->d_bs_class;
   }
+  if (nuc > 1) {
+    cudaError_t e = cudaMalloc(&env->d_ue_class, cfg->num_ues);
+    if (e == cudaSuccess) e = cudaMemcpy(env->d_ue_class, cfg->ue_class, cfg->num_ues, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      mbe_destroy(env);
+      return fail("mbe_create: ue_class upload failed: %s", cudaGetErrorString(e));
+    }
+    a.ue_class = env->d_ue_class;
+  }
   for (int b = 0; b < mbe::kMaxSlots; ++b) {
     const int c = (cfg->bs_class && b < cfg->num_bs) ? cfg->bs_class[b] : 0;
-    const mbe::ClassDev& d = a.cls[c];
+    const mbe::ClassDev& d = a.cls[c * nuc];  // (the slot table serves the one-UE-class kernels)
     mbe::SlotDev& sl = a.slot[b];
     sl.x = sl.y = 0;  // coordinates of a shared layout arrive with mbe_bind (host copy of bs_xy)
     sl.d2max = d.d2max;
@@ -323,8 +378,10 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     sl.xf = sl.yf = 0.0f;
     sl.lutn = d.lutn;
   }
-  // the specialised kernels assume one BS class and squared distances exact in FP32
-  const bool spec_ok = cfg->num_classes == 1 &&
+  // the specialised kernels assume one UE class, log2 snr affine in log-distance and squared
+  // distances exact in FP32; the warp-segment ones take per-BS classes (folded per slot), the
+  // UEs-per-thread and thread-per-env ones a single class
+  const bool spec_ok = nuc == 1 && !any_ltab &&
                        std::floor(cfg->width) * std::floor(cfg->width) + std::floor(cfg->height) * std::floor(cfg->height) <
                            16777216.0;
   if (spec_ok && !(cfg->flags & MBE_FLAG_GENERIC_KERNEL)) {
@@ -343,7 +400,8 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   {
     const char* v = std::getenv("MBE_UPT");
     const bool on = !(v && v[0] == '0');
-    if (on && spec_ok && gym && !a.bs_per_env && !env->big && !(cfg->flags & MBE_FLAG_GENERIC_KERNEL))
+    if (on && spec_ok && cfg->num_classes == 1 && gym && !a.bs_per_env && !env->big &&
+        !(cfg->flags & MBE_FLAG_GENERIC_KERNEL))
       for (const UptEntry& t : kUpts)
         if (t.handler == cfg->handler && t.U == a.U && t.B == a.B) {
           env->upt = t.fn;
@@ -354,7 +412,7 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   {
     const char* v = std::getenv("MBE_TPE");
     const bool on = !(v && v[0] == '0');
-    if (on && !gym && a.bs_per_env && cfg->num_classes == 1 && !env->big && a.E % 32 == 0 && a.U == 7 && a.B == 10 &&
+    if (on && !gym && a.bs_per_env && spec_ok && cfg->num_classes == 1 && !env->big && a.E % 32 == 0 && a.U == 7 && a.B == 10 &&
         cfg->width <= 2048 && cfg->height <= 2048 &&
         !(cfg->flags & MBE_FLAG_GENERIC_KERNEL)) {
       env->tpe = mbe::step_tpe_fork_kernel<7, 10>;
@@ -429,8 +487,9 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
 
 void mbe_destroy(mbe_env* env) {
   if (!env) return;
-  for (double* p : env->luts) cudaFree(p);
+  for (void* p : env->luts) cudaFree(p);
   if (env->d_bs_class) cudaFree(env->d_bs_class);
+  if (env->d_ue_class) cudaFree(env->d_ue_class);
   if (env->host_stream) cudaStreamDestroy(env->host_stream);
   if (env->host_fork) cudaEventDestroy(env->host_fork);
   if (env->host_join) cudaEventDestroy(env->host_join);

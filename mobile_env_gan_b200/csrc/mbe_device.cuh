@@ -17,21 +17,34 @@ constexpr int kMaxSlots = 32;
 enum Op : int { OP_STEP = 0, OP_RESET = 1, OP_OBSERVE = 2 };
 enum Purpose : unsigned { P_WAYPOINT = 0, P_INITPOS = 1, P_BSLAYOUT = 2 };
 
-// One BS class (include/mbe.h mbe_bs_class) as the kernels see it.
+// One link class (include/mbe.h mbe_link_class: a BS parameter set x a UE parameter set) as the
+// kernels see it.  Link class of the pair (b, u) = bs_class[b] * n_ue_classes + ue_class[u].
 struct ClassDev {
   float l0_hi, l0_lo;  // log2 snr at d2 = 1, split hi+lo (channel kernel keeps ~2^-30 of it)
   float k_hi, k_lo;    // slope per log2(d2)
   float l_zero;        // log2 snr at d2 == 0
   int d2max;           // connectable iff d2 <= d2max
   int stride;          // d2max + 1
-  int pad;
+  int ltab_len;
   // lutn[n*stride + d2] = round(rate_lut[d2] / n, 2) for n >= 1: Channel.datarate
   // (channels.py:78-83) split over n UEs (schedules.py:20-22) and rounded like base.py:435, all
   // in FP64.  Row n = 0 does not exist: the pointer is biased so that lutn[stride - 1] is a
   // 0.0 entry placed just before row 1 (an unconnected link adds exactly nothing).
   const double* lutn;
   const double* lut0;  // rate_lut[d2] itself (un-split, un-rounded) for the block-per-env kernel
+  const float* ltab;   // log2 snr per d2 for losses that are not affine in log-distance, else nullptr
 };
+
+// Movement parameters of one UE class (include/mbe.h mbe_ue_class), folded on the host.
+struct MoveDev {
+  double velocity;
+  float velocity_f, tie_eps;  // FP32 fast path of the movement and its fallback band
+  int axis_exact;             // (velocity*d)/|d| == +-velocity in FP64 for every |d| on the map
+  int move_d2max;             // largest integer d2 with sqrt(d2) <= velocity (movement.py:54)
+};
+
+constexpr int kMaxLinkClasses = 16;
+constexpr int kMaxUeClasses = 8;
 
 // One BS slot of a shared layout with its class folded in: every field becomes a constant-bank
 // operand once the specialised kernels unroll their loops over b.
@@ -52,19 +65,19 @@ struct StepArgs {
   // scenario
   int ep_time, autoreset, reset_rng_episode, bs_per_env, bs_rand_min, bs_rand_max;
   unsigned seed_lo, seed_hi;
-  double width, height, velocity;
-  float velocity_f, tie_eps;  // FP32 fast path of the movement and its fallback band
-  int axis_exact;             // (velocity*d)/|d| == +-velocity in FP64 for every |d| on the map
+  double width, height;
   int wh_int, wh_int_w, wh_int_h;  // width and height are integers (the usual case): integer draws
-  int move_d2max;
+  MoveDev mv[kMaxUeClasses];       // [0] is the only one when all UEs are alike
   // utility: u = clip(util_c * log2(w2 + r), lo, hi); scaled = (u - lo) * util_scale - 1
   float util_c, util_w2, util_lo, util_hi, util_scale;
   float inv_U;  // 1/U for the per-env means
-  int n_classes;
+  int n_classes;     // BS classes
+  int n_ue_classes;  // UE classes (>= 1)
   int scheduler;  // 0 ResourceFair; 1 ProportionalFair, 2 RateFair (block-per-env kernel only)
-  ClassDev cls[8];
+  ClassDev cls[kMaxLinkClasses];  // [bs class * n_ue_classes + ue class]
   SlotDev slot[kMaxSlots];
   const uint8_t* bs_class;  // device [B] or nullptr
+  const uint8_t* ue_class;  // device [U] or nullptr (all UEs class 0)
   // bound buffers (see include/mbe.h)
   uint32_t* pos;
   uint32_t* wp;
@@ -217,32 +230,32 @@ __device__ __forceinline__ void next_waypoint(const StepArgs& a, unsigned gid, u
 // only when t lies within tie_eps of a rounding tie is the reference's FP64 chain replayed, so
 // the integer result is always the reference's.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void move_slow(const StepArgs& a, int& x, int& y, int dx, int dy, int d2) {
+__device__ __forceinline__ void move_slow(const MoveDev& m, int& x, int& y, int dx, int dy, int d2) {
   double norm = sqrt((double)d2);
-  x = (int)rint((double)x + (a.velocity * (double)dx) / norm);
-  y = (int)rint((double)y + (a.velocity * (double)dy) / norm);
+  x = (int)rint((double)x + (m.velocity * (double)dx) / norm);
+  y = (int)rint((double)y + (m.velocity * (double)dy) / norm);
 }
 
-__device__ __forceinline__ bool move_ue(const StepArgs& a, int& x, int& y, int wx, int wy) {
+__device__ __forceinline__ bool move_ue(const MoveDev& m, int& x, int& y, int wx, int wy) {
   int dx = wx - x, dy = wy - y;
   int d2 = dx * dx + dy * dy;
-  if (d2 <= a.move_d2max) {
+  if (d2 <= m.move_d2max) {
     x = wx;
     y = wy;
     return true;  // arrived: snap and pop the waypoint (movement.py:54-56)
   }
-  float s = a.velocity_f * rsqrtf((float)d2);
+  float s = m.velocity_f * rsqrtf((float)d2);
   float tx = (float)dx * s, ty = (float)dy * s;
   float rx = rintf(tx), ry = rintf(ty);
   float worst = fmaxf(fabsf(tx - rx), fabsf(ty - ry));  // distance to the nearest integer, <= 0.5
-  if (worst > 0.5f - a.tie_eps) {
-    if (a.axis_exact && (dx == 0 || dy == 0)) {
+  if (worst > 0.5f - m.tie_eps) {
+    if (m.axis_exact && (dx == 0 || dy == 0)) {
       // axis-aligned (frequent: integer snapping lines UEs up with their waypoint): the FP64
       // step is exactly +-velocity (host-verified), so only the final rint needs FP64
-      if (dx != 0) x = (int)rint((double)x + (dx > 0 ? a.velocity : -a.velocity));
-      if (dy != 0) y = (int)rint((double)y + (dy > 0 ? a.velocity : -a.velocity));
+      if (dx != 0) x = (int)rint((double)x + (dx > 0 ? m.velocity : -m.velocity));
+      if (dy != 0) y = (int)rint((double)y + (dy > 0 ? m.velocity : -m.velocity));
     } else {
-      move_slow(a, x, y, dx, dy, d2);
+      move_slow(m, x, y, dx, dy, d2);
     }
   } else {
     x += (int)rx;
@@ -251,8 +264,10 @@ __device__ __forceinline__ bool move_ue(const StepArgs& a, int& x, int& y, int w
   return false;
 }
 
-// log2 of the SNR (channels.py:24-27 + 132-146 folded): l0 - k*log2(d2); SFU lg2 on FP32.
+// log2 of the SNR (channels.py:24-27 + 132-146 folded): l0 - k*log2(d2); SFU lg2 on FP32.  Losses
+// that are not affine in log-distance come as a table over d2 (Channel.fold).
 __device__ __forceinline__ float log2_snr(const ClassDev& c, int d2) {
+  if (c.ltab) return c.ltab[min(d2, c.ltab_len - 1)];
   if (d2 == 0) return c.l_zero;
   float lg = lg2_sfu((float)d2);
   float l = fmaf(-c.k_hi, lg, c.l0_hi);
@@ -266,6 +281,11 @@ __device__ __forceinline__ float log2_snr_obs_f(float k, float l0, float d2f) {
   return fmaf(-k, lg2_sfu(fmaxf(d2f, 1e-32f)), l0);
 }
 __device__ __forceinline__ float log2_snr_obs(float k, float l0, int d2) { return log2_snr_obs_f(k, l0, (float)d2); }
+// the same for any link class (runtime-shape kernels)
+__device__ __forceinline__ float log2_snr_obs(const ClassDev& c, int d2) {
+  if (c.ltab) return c.ltab[min(d2, c.ltab_len - 1)];
+  return log2_snr_obs_f(c.k_hi, c.l0_hi, (float)d2);
+}
 
 // BoundedLogUtility.calculateUtility + scaleUtility (utilities.py:44-55); SFU lg2
 // (absolute error 2^-22 near 1, relative 2^-22 elsewhere).

@@ -77,6 +77,11 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
   const size_t idx = (size_t)env * U + u;
   const unsigned gid = a.env_offset + (unsigned)env;
   const uint32_t* bs_tab = a.bs_per_env ? (s.bs + (size_t)min(env_in_blk, a.epb - 1) * B) : s.bs;
+  // link class of (b, this UE) = bs_class[b] * n_ue_classes + ue_class[u] (entities.py:6-57)
+  const int ucls = a.ue_class ? (int)a.ue_class[min(u, U - 1)] : 0;
+  const int nuc = a.n_ue_classes;
+  auto link = [&](int b) -> const ClassDev& { return a.cls[(int)s.cls[b] * nuc + ucls]; };
+  const MoveDev& mv = a.mv[ucls];
 
   const int op = a.op;
   int ph = a.phases;
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
                      wx, wy);
       }
     }
-    if (move_ue(a, x, y, wx, wy)) wx = wy = -1;
+    if (move_ue(mv, x, y, wx, wy)) wx = wy = -1;
   };
 
   // ---- PRE (FORK): nearest connectable BS, ResourceFair split, utility (base.py:236-258) ----
@@ -151,7 +156,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     if (valid) {
       for (int b = 0; b < nb; ++b) {
         int d2 = d2_to(b);
-        if (d2 <= a.cls[s.cls[b]].d2max && d2 < bestd2) {  // strict <: first minimum wins (base.py:240)
+        if (d2 <= link(b).d2max && d2 < bestd2) {  // strict <: first minimum wins (base.py:240)
           best = b;
           bestd2 = d2;
         }
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     double rate = 0.0;
     if (valid && best >= 0) {
       int n = __popc(peers);
-      const ClassDev& c = a.cls[s.cls[best]];
+      const ClassDev& c = link(best);
       rate = c.lutn[(size_t)n * c.stride + bestd2];  // schedules.py:20-22, base.py:435
     }
     util = scaled_utility(a, rate);
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
       }
       if (a.dbg_snr) {
         for (int b = 0; b < B; ++b)
-          a.dbg_snr[idx * B + b] = (b < nb) ? ex2_sfu(log2_snr(a.cls[s.cls[b]], d2_to(b))) : 0.0f;
+          a.dbg_snr[idx * B + b] = (b < nb) ? ex2_sfu(log2_snr(link(b), d2_to(b))) : 0.0f;
       }
     }
   };
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
   auto phase_pre_gym = [&]() {
     if (valid) {
       for (int b = 0; b < nb; ++b)
-        if (d2_to(b) <= a.cls[s.cls[b]].d2max) elig_pre |= 1u << b;  // check_connectivity (base.py:212-214)
+        if (d2_to(b) <= link(b).d2max) elig_pre |= 1u << b;  // check_connectivity (base.py:212-214)
       conn &= elig_pre;  // update_connections (base.py:221-227)
       int act = a.actions[idx];
       if (act > 0 && act <= nb) {  // NOOP_ACTION = 0 (base.py:29)
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
       unsigned m = __ballot_sync(kFull, bit) & segmask;
       if (bit) {  // allocateDataRate2User (base.py:421-435), bs-major accumulation (413-418)
         int n = __popc(m);
-        const ClassDev& c = a.cls[s.cls[b]];
+        const ClassDev& c = link(b);
         rate += c.lutn[(size_t)n * c.stride + d2_to(b)];
       }
     }
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     }
     if (valid && a.dbg_snr) {
       for (int b = 0; b < B; ++b)
-        a.dbg_snr[idx * B + b] = (b < nb) ? ex2_sfu(log2_snr(a.cls[s.cls[b]], d2_to(b))) : 0.0f;
+        a.dbg_snr[idx * B + b] = (b < nb) ? ex2_sfu(log2_snr(link(b), d2_to(b))) : 0.0f;
     }
   };
 
@@ -282,9 +287,9 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     float lmax = -INFINITY;
     uint32_t elig = 0;
     for (int b = 0; b < nb; ++b) {
-      const ClassDev& c = a.cls[s.cls[b]];
+      const ClassDev& c = link(b);
       int d2 = d2_to(b);
-      float l = log2_snr_obs(c.k_hi, c.l0_hi, d2);
+      float l = log2_snr_obs(c, d2);
       row[B + b] = l;
       lmax = fmaxf(lmax, l);
       if (d2 <= c.d2max) elig |= 1u << b;
@@ -386,7 +391,7 @@ __global__ void __launch_bounds__(kThreads) channel_kernel(const __grid_constant
       int bx, by;
       unpack_xy(tab[b], bx, by);
       int dx = x - bx, dy = y - by, d2 = dx * dx + dy * dy;
-      const ClassDev& c = a.cls[scls[b]];
+      const ClassDev& c = a.cls[(int)scls[b] * a.n_ue_classes + (a.ue_class ? (int)a.ue_class[idx % U] : 0)];
       snr = ex2_sfu(log2_snr(c, d2));
       if (d2 <= c.d2max) elig |= 1u << b;
     }

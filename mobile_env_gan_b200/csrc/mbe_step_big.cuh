@@ -111,8 +111,17 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
     }
   }
   bool done = false, fresh = false;
-  const bool one_class = a.n_classes == 1;
+  const bool one_class = a.n_classes == 1 && a.n_ue_classes == 1;
   const int d2max0 = a.cls[0].d2max;
+  // link class of (b, UE i of this thread) = bs_class[b] * n_ue_classes + ue_class[u] (entities.py:6-57)
+  int ucls[kBigMaxI];
+#pragma unroll
+  for (int i = 0; i < kBigMaxI; ++i) {
+    const int u = tid + i * kBigThreads;
+    ucls[i] = (a.ue_class && u < U) ? (int)a.ue_class[u] : 0;
+  }
+  const int nuc = a.n_ue_classes;
+  auto link = [&](int i, int b) -> const ClassDev& { return a.cls[(int)s.cls[b] * nuc + ucls[i]]; };
 
   auto d2_to = [&](int i, int b) {
     int bx, by;
@@ -128,7 +137,7 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
       const int u = tid + i * kBigThreads;
       if (u >= U) continue;
       if (wx[i] < 0) next_waypoint(a, gid, (unsigned)u, (size_t)env * U + u, t_e, epi, true, wx[i], wy[i]);
-      if (move_ue(a, x[i], y[i], wx[i], wy[i])) wx[i] = wy[i] = -1;
+      if (move_ue(a.mv[ucls[i]], x[i], y[i], wx[i], wy[i])) wx[i] = wy[i] = -1;
     }
   };
 
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
         const int b_lo = 32 * w, b_hi = min(nb, 32 * w + 32);
         for (int b = b_lo; b < b_hi; ++b) {
           const int d2 = d2_to(i, b);
-          if (d2 <= (one_class ? d2max0 : a.cls[s.cls[b]].d2max)) {  // check_connectivity (base.py:212-214)
+          if (d2 <= (one_class ? d2max0 : link(i, b).d2max)) {  // check_connectivity (base.py:212-214)
             ew |= 1u << (b - b_lo);
             if (!GYM && d2 < bestd2[i]) {  // nearest connectable BS, first minimum (base.py:240)
               best[i] = b;
@@ -260,10 +269,10 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
           m &= m - 1;
           atomicAdd(&s.cnt[b], 1);
           if (a.scheduler == 1) {
-            const double raw = a.cls[s.cls[b]].lut0[d2_to(i, b)];
+            const double raw = link(i, b).lut0[d2_to(i, b)];
             atomicAdd(&s.pf_tot[b], (unsigned long long)__double2ll_rn(raw * 1048576.0));
           } else if (a.scheduler == 2) {
-            const double raw = a.cls[s.cls[b]].lut0[d2_to(i, b)];
+            const double raw = link(i, b).lut0[d2_to(i, b)];
             atomicAdd(&s.pf_tot[b], (unsigned long long)__double2ll_rn(0x1p50 / raw));
           }
         }
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
         while (m) {  // ascending bs order = the reference's bs-major accumulation
           const int b = (__ffs(m) - 1) + 32 * w;
           m &= m - 1;
-          r += link_share(a, a.cls[s.cls[b]], d2_to(i, b), s.cnt[b], s.pf_tot[b]);
+          r += link_share(a, link(i, b), d2_to(i, b), s.cnt[b], s.pf_tot[b]);
         }
       }
       rate[i] = r;
@@ -398,9 +407,9 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
       uint32_t k0 = 0, k1 = 0;
       if (active)
         for (int b = 0; b < nb; ++b) {
-          const ClassDev& c = a.cls[s.cls[b]];
+          const ClassDev& c = link(i, b);
           const int d2 = d2_to(i, b);
-          const float l = log2_snr_obs(c.k_hi, c.l0_hi, d2);
+          const float l = log2_snr_obs(c, d2);
           tile[lane][b] = l;
           lmax = fmaxf(lmax, l);
           if (d2 <= c.d2max) {

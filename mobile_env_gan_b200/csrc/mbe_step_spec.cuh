@@ -89,7 +89,9 @@ __device__ __forceinline__ void step_chunk(const StepArgs& a, const int env_base
   const unsigned idx = (unsigned)env_ld * U + (valid ? u : 0);
   const unsigned gid = a.env_offset + (unsigned)env;
   uint32_t* bs_env = PER_ENV ? s_bs + (size_t)min(env_in_blk, EPB - 1) * B : nullptr;
-  const SlotDev& C0 = a.slot[0];  // the single BS class
+  // the slot's class constants (BSs of a shared layout may differ in bw/freq/tx/height,
+  // entities.py:6-29; per-env random layouts have one class): constant-bank operands once unrolled
+  auto SL = [&](int b) -> const SlotDev& { return a.slot[PER_ENV ? 0 : b]; };
 
   // ---- load state (all loads issued before any use) ----
   const unsigned lidx = valid ? (unsigned)(env_in_blk * U + u) : 0u;  // index inside the chunk
@@ -134,7 +136,7 @@ __device__ __forceinline__ void step_chunk(const StepArgs& a, const int env_base
 
   auto phase_move = [&]() {
     if (wx < 0) next_waypoint(a, gid, (unsigned)u, idx, t_e, epi, valid, wx, wy);  // movement.py:44-47
-    if (move_ue(a, x, y, wx, wy)) wx = wy = -1;
+    if (move_ue(a.mv[0], x, y, wx, wy)) wx = wy = -1;
   };
 
   auto phase_clock = [&]() {
@@ -153,7 +155,7 @@ __device__ __forceinline__ void step_chunk(const StepArgs& a, const int env_base
 #pragma unroll
     for (int b = 0; b < B; ++b) {
       int d2 = d2_to(b);
-      bool ok = (d2 <= C0.d2max) && (d2 < bestd2);  // strict <: first minimum wins (base.py:240)
+      bool ok = (d2 <= SL(b).d2max) && (d2 < bestd2);  // strict <: first minimum wins (base.py:240)
       if (PER_ENV) ok = ok && (b < nb);
       if (ok) {
         best = b;
@@ -163,7 +165,10 @@ __device__ __forceinline__ void step_chunk(const StepArgs& a, const int env_base
     const bool has = valid && best >= 0;
     unsigned peers = __match_any_sync(kFull, has ? (seg * 64 + best) : (0x10000 + lane));
     double rate = 0.0;
-    if (has) rate = C0.lutn[(unsigned)__popc(peers) * (unsigned)C0.stride + (unsigned)bestd2];
+    if (has) {
+      const SlotDev& sb = SL(best);
+      rate = sb.lutn[(unsigned)__popc(peers) * (unsigned)sb.stride + (unsigned)bestd2];
+    }
     util = scaled_utility(a, rate);
     if (valid) {
       a.assoc[idx] = best;
@@ -187,7 +192,7 @@ __device__ __forceinline__ void step_chunk(const StepArgs& a, const int env_base
 #pragma unroll
     for (int b = 0; b < B; ++b) {
       d2pre[b] = d2_to(b);
-      bool ok = d2pre[b] <= C0.d2max;  // check_connectivity (base.py:212-214)
+      bool ok = d2pre[b] <= SL(b).d2max;  // check_connectivity (base.py:212-214)
       if (PER_ENV) ok = ok && (b < nb);
       elig |= ok ? (1u << b) : 0u;
     }
@@ -206,13 +211,12 @@ __device__ __forceinline__ void step_chunk(const StepArgs& a, const int env_base
       cnt[b] = __popc(__ballot_sync(kFull, (conn >> b) & 1u) & segmask);
       csum_i += cnt[b];
     }
-    const double* lut = C0.lutn;
-    const unsigned stride = (unsigned)C0.stride;
     double rate = 0.0;
 #pragma unroll
     for (int b = 0; b < B; ++b) {
+      const unsigned stride = (unsigned)SL(b).stride;
       unsigned off = (unsigned)cnt[b] * stride + (unsigned)d2pre[b];
-      rate += lut[((conn >> b) & 1u) ? off : stride - 1u];
+      rate += SL(b).lutn[((conn >> b) & 1u) ? off : stride - 1u];
     }
     util = scaled_utility(a, rate);
     float usum = seg_sum_head<U>(valid ? util : 0.0f, u);
@@ -297,11 +301,11 @@ __device__ __forceinline__ void step_chunk(const StepArgs& a, const int env_base
           }
           float dx = xf - bxf, dy = yf - byf;
           float d2f = fmaf(dx, dx, dy * dy);  // exact: integers below 2^24
-          l[b] = log2_snr_obs_f(C0.k, C0.l0, d2f);
+          l[b] = log2_snr_obs_f(SL(b).k, SL(b).l0, d2f);
           bool live = !PER_ENV || (b < nb);
           if (!live) l[b] = -INFINITY;
           lmax = fmaxf(lmax, l[b]);
-          if (MA && live && d2f <= (float)C0.d2max) elig2 |= 1u << b;
+          if (MA && live && d2f <= (float)SL(b).d2max) elig2 |= 1u << b;
         }
 #pragma unroll
         for (int b = 0; b < B; ++b) {

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(32, ROLLOUT ? MBE_TPE_ROLLOUT_BLOCKS : MBE_TPE
     int x, y, wx, wy;
     unpack_xy(my_pos[u], x, y);
     unpack_xy(my_wp[u], wx, wy);
-    if (move_ue(a, x, y, wx, wy)) wx = wy = -1;
+    if (move_ue(a.mv[0], x, y, wx, wy)) wx = wy = -1;
     my_pos[u] = pack_xy(x, y);
     my_wp[u] = pack_xy(wx, wy);
     if constexpr (ROLLOUT) {

@@ -28,7 +28,49 @@
 #define MBE_UPT_WARPS 2
 #endif
 
+// experiment switches (profiles/variant_sweep.py): cache hints for the streamed state / the rate table
+#ifndef MBE_UPT_STREAM_HINTS
+#define MBE_UPT_STREAM_HINTS 0
+#endif
+// how the observation block leaves shared memory: 0 = one bulk async copy per CTA (thread 0 issues
+// and waits for the read), 1 = cooperative 16-byte copies by the whole CTA after a barrier,
+// 2 = every warp copies its own envs (8-byte units, no CTA barrier)
+#ifndef MBE_UPT_STORE
+#define MBE_UPT_STORE 0
+#endif
+#ifndef MBE_UPT_LUT_HINT
+#define MBE_UPT_LUT_HINT 2  // read-only path for the rate table: measured -2.3% (multi-agent), neutral (central)
+#endif
+
 namespace mbe {
+
+template <typename T>
+__device__ __forceinline__ T upt_ld(const T* p) {
+#if MBE_UPT_STREAM_HINTS
+  return __ldcs(p);  // read once: do not keep the line
+#else
+  return *p;
+#endif
+}
+template <typename T>
+__device__ __forceinline__ void upt_st(T* p, T v) {
+#if MBE_UPT_STREAM_HINTS
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+__device__ __forceinline__ double upt_lut(const double* p) {
+#if MBE_UPT_LUT_HINT == 1
+  double v;
+  asm("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#elif MBE_UPT_LUT_HINT == 2
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
 
 template <int HANDLER, int U, int B, int K>
 __host__ __device__ constexpr size_t upt_smem_bytes() {
@@ -77,10 +119,10 @@ __global__ void __launch_bounds__(32 * MBE_UPT_WARPS, MBE_UPT_MIN_BLOCKS(HANDLER
 #pragma unroll
   for (int j = 0; j < UPT; ++j) {
     idx[j] = (unsigned)env_ld * U + (unsigned)(k + K * j);
-    pos_in[j] = a.pos[idx[j]];
-    wp_in[j] = a.wp[idx[j]];
-    conn[j] = valid ? a.conn[idx[j]] : 0u;
-    act[j] = valid ? a.actions[idx[j]] : 0;
+    pos_in[j] = upt_ld(a.pos + idx[j]);
+    wp_in[j] = upt_ld(a.wp + idx[j]);
+    conn[j] = valid ? upt_ld(a.conn + idx[j]) : 0u;
+    act[j] = valid ? upt_ld(a.actions + idx[j]) : 0;
   }
   int t_e = a.t[env_ld];
   int epi = a.episode[env_ld];
@@ -108,12 +150,13 @@ __global__ void __launch_bounds__(32 * MBE_UPT_WARPS, MBE_UPT_MIN_BLOCKS(HANDLER
       elig[j] |= (d2pre[j][b] <= C0.d2max) ? (1u << b) : 0u;  // check_connectivity (base.py:212-214)
     }
     conn[j] &= elig[j];
-    if (act[j] > 0 && act[j] <= B) {
-      const uint32_t bit = 1u << (act[j] - 1);
-      conn[j] = (conn[j] & bit) ? (conn[j] & ~bit) : (conn[j] | (elig[j] & bit));
+    {  // toggle BS act-1: disconnect when connected, else connect when connectable (one XOR)
+      const uint32_t bit = ((unsigned)(act[j] - 1) < (unsigned)B) ? (1u << (act[j] - 1)) : 0u;
+      conn[j] ^= bit & (conn[j] | elig[j]);
     }
+    // 4 connection bits -> 4 byte counters: bit i lands on bit 8i of (nibble * 0x204081), no collisions
 #pragma unroll
-    for (int b = 0; b < B; ++b) packed[b >> 2] += ((conn[j] >> b) & 1u) << (8 * (b & 3));
+    for (int w = 0; w < NW; ++w) packed[w] += (((conn[j] >> (4 * w)) & 0xfu) * 0x00204081u) & 0x01010101u;
   }
   uint32_t tot[NW];
 #pragma unroll
@@ -143,10 +186,10 @@ __global__ void __launch_bounds__(32 * MBE_UPT_WARPS, MBE_UPT_MIN_BLOCKS(HANDLER
 #pragma unroll
     for (int b = 0; b < B; ++b) {
       if (MA) {  // measured: predicated gathers win with the multi-agent register budget ...
-        if ((conn[j] >> b) & 1u) r += lut[(unsigned)cnt[b] * stride + (unsigned)d2pre[j][b]];
+        if ((conn[j] >> b) & 1u) r += upt_lut(lut + ((unsigned)cnt[b] * stride + (unsigned)d2pre[j][b]));
       } else {   // ... unconditional ones (unconnected -> the table's 0.0 entry) for the central handler
         const unsigned off = (unsigned)cnt[b] * stride + (unsigned)d2pre[j][b];
-        r += lut[((conn[j] >> b) & 1u) ? off : stride - 1u];
+        r += upt_lut(lut + (((conn[j] >> b) & 1u) ? off : stride - 1u));
       }
     }
     rate[j] = r;
@@ -180,8 +223,8 @@ __global__ void __launch_bounds__(32 * MBE_UPT_WARPS, MBE_UPT_MIN_BLOCKS(HANDLER
   if (valid) {
 #pragma unroll
     for (int j = 0; j < UPT; ++j) {
-      if (a.rate) a.rate[idx[j]] = rate[j];
-      a.utility[idx[j]] = util[j];
+      if (a.rate) upt_st(a.rate + idx[j], rate[j]);
+      upt_st(a.utility + idx[j], util[j]);
       if (MA) {
         float nu = 0.0f;
         int ncnt = 0;
@@ -207,7 +250,7 @@ __global__ void __launch_bounds__(32 * MBE_UPT_WARPS, MBE_UPT_MIN_BLOCKS(HANDLER
 #pragma unroll
   for (int j = 0; j < UPT; ++j) {
     if (wx[j] < 0) next_waypoint(a, gid, (unsigned)(k + K * j), idx[j], t_e, epi, valid, wx[j], wy[j]);
-    if (move_ue(a, x[j], y[j], wx[j], wy[j])) wx[j] = wy[j] = -1;
+    if (move_ue(a.mv[0], x[j], y[j], wx[j], wy[j])) wx[j] = wy[j] = -1;
   }
 
   // ---- clock, departures, same-step autoreset (base.py:280-291, 407-409; 172-209) ----
@@ -253,10 +296,12 @@ __global__ void __launch_bounds__(32 * MBE_UPT_WARPS, MBE_UPT_MIN_BLOCKS(HANDLER
 #pragma unroll
       for (int b = 0; b < B; ++b) {
         const float dx = xf - a.slot[b].xf, dy = yf - a.slot[b].yf;
-        const float d2f = fmaf(dx, dx, dy * dy);  // exact: integers below 2^24
-        l[b] = log2_snr_obs_f(C0.k, C0.l0, d2f);
+        // exact: integers below 2^24; the 1e-32 (d = 0 is the reference's EPSILON, channels.py:8) vanishes
+        // in the rounding of every d2 >= 1
+        const float d2f = fmaf(dx, dx, fmaf(dy, dy, 1e-32f));
+        l[b] = fmaf(-C0.k, lg2_sfu(d2f), C0.l0);
         lmax = fmaxf(lmax, l[b]);
-        if (MA && d2f <= (float)C0.d2max) elig2 |= 1u << b;
+        if (MA && d2f <= (float)C0.d2max) elig2 |= 1u << b;  // (d2max + 1e-32 rounds to d2max)
       }
 #pragma unroll
       for (int b = 0; b < B; ++b) {
@@ -292,6 +337,35 @@ __global__ void __launch_bounds__(32 * MBE_UPT_WARPS, MBE_UPT_MIN_BLOCKS(HANDLER
     }
     if (k == 0) a.t[env] = t_e;
   }
+#if MBE_UPT_STORE == 1
+  if (a.obs_bulk_ok && env_base + EPB <= a.E) {
+    constexpr int N16 = EPB * U * F / 4;
+    static_assert((EPB * U * F) % 4 == 0, "whole CTA blocks are multiples of 16 bytes");
+    __syncthreads();
+    float4* g = reinterpret_cast<float4*>(a.obs + (size_t)env_base * (U * F));
+    const float4* sv = reinterpret_cast<const float4*>(s_obs);
+#pragma unroll
+    for (int i = 0; i < (N16 + 32 * MBE_UPT_WARPS - 1) / (32 * MBE_UPT_WARPS); ++i) {
+      const int e = tid + i * 32 * MBE_UPT_WARPS;
+      if (e < N16) g[e] = sv[e];
+    }
+    return;
+  }
+#elif MBE_UPT_STORE == 2
+  if (a.obs_bulk_ok && env_base + EPB <= a.E) {
+    constexpr int N8 = EPW * U * F / 2;  // 8-byte units of one warp's envs
+    static_assert((EPW * U * F) % 2 == 0, "a warp's rows are a multiple of 8 bytes");
+    __syncwarp();
+    float2* g = reinterpret_cast<float2*>(a.obs + (size_t)(env_base + warp * EPW) * (U * F));
+    const float2* sv = reinterpret_cast<const float2*>(s_obs + warp * EPW * U * F);
+#pragma unroll
+    for (int i = 0; i < (N8 + 31) / 32; ++i) {
+      const int e = lane + i * 32;
+      if (e < N8) g[e] = sv[e];
+    }
+    return;
+  }
+#endif
   store_obs_block<32 * MBE_UPT_WARPS>(a, s_obs, env_base, tid, true);
 }
 

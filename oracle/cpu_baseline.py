@@ -118,7 +118,7 @@ def _compiled_worker(args):
     bs, U, mode, handler, vel, over = WORKLOADS[workload]
     p = orc.Params(velocity=vel, **over)
     rng = np.random.default_rng(7)
-    envs = max(64, min(envs, (1 << 22) // (U * len(bs or [0] * 10))))  # bound the wide shapes' memory and time
+    envs = min(envs, max(64, (1 << 22) // (U * len(bs or [0] * 10))))  # bound the wide shapes' memory and time
     E = envs
     if bs is None:  # the fork's scenario: 5..10 random BSs per env (custom.py:68-77)
         layout = rng.integers(0, 200, size=(E, 10, 2)).astype(np.int32)

@@ -93,7 +93,9 @@ def test_compiled_cpu_baseline_runs_bounded():
 
     out = cpu_baseline.run_compiled("mobile-small-central-v0", 0.2, envs=256)
     assert out["value"] > 0 and out["kind"].startswith("port (compiled C") and out["cores"] >= 1
-    assert cpu_baseline.run_compiled("mobile-synthetic-central-v0", 0.2) is None  # not in the baseline's workload table
+    wide = cpu_baseline.run_compiled("mobile-synthetic-central-v0", 0.2)  # 64 x 512 ProportionalFair
+    assert wide["value"] > 0 and "128 envs" in wide["sample"]  # env count bounded for the wide shape
+    assert cpu_baseline.run_compiled("no-such-workload-v0", 0.2) is None  # not in the baseline's workload table
     bad = cpu_baseline.run_compiled("mobile-small-central-v0", 0.2, envs=-5)
     assert "unavailable" in bad
 

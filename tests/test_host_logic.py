@@ -110,10 +110,19 @@ def test_unsupported_plugins_fail_loudly():
     cfg = MComCore.seeding(deep_dict_merge(MComCore.default_config(), {"movement": Teleport}))
     with pytest.raises(NotImplementedError):
         MComCore.build_plan(stations, users, cfg)
-    users2 = users + [UserEquipment(1, velocity=3, snr_tr=2e-8, noise=1e-9, height=1.6)]
+    # heterogeneous UEs (entities.py:32-57 keeps velocity / snr_tr / noise / height per UE) become UE classes
+    users2 = users + [UserEquipment(1, velocity=3, snr_tr=2e-8, noise=1e-9, height=1.6),
+                      UserEquipment(2, velocity=3, snr_tr=1e-7, noise=1e-9, height=1.6),
+                      UserEquipment(3, **cfg["ue"])]
     cfg = MComCore.seeding(MComCore.default_config())
+    plan = MComCore.build_plan(stations, users2, cfg)
+    assert plan.ue_class.tolist() == [0, 1, 2, 0] and len(plan.ue_classes) == 3 and len(plan.classes) == 3
+    assert [c["velocity"] for c in plan.ue_classes] == [1.5, 3.0, 3.0]
+    assert plan.classes[0] is plan.classes[1]  # same radio parameters, other speed: one fold
+    assert plan.classes[2]["d2max"] < plan.classes[0]["d2max"]  # higher threshold: shorter range
+    many = [UserEquipment(i, velocity=1.0 + i, snr_tr=2e-8, noise=1e-9, height=1.6) for i in range(9)]
     with pytest.raises(NotImplementedError):
-        MComCore.build_plan(stations, users2, cfg)
+        MComCore.build_plan(stations, many, cfg)
 
 
 def test_library_exports_every_declared_symbol():
@@ -128,8 +137,12 @@ def test_library_exports_every_declared_symbol():
     assert lib.mbe_abi_version() == _lib.MBE_ABI_VERSION
     assert b"sm_100a" in lib.mbe_build_info()
     # struct sizes the binding assumes (LP64)
-    assert ctypes.sizeof(_lib.BsClass) == 40
+    assert ctypes.sizeof(_lib.BsClass) == 48
     assert ctypes.sizeof(_lib.Buffers) == 18 * 8 + 8
+    # ... and the library reports the same layout (checked again by _lib.load on every import)
+    for which, struct in enumerate((_lib.Config, _lib.Buffers, _lib.BsClass, _lib.UeClass, _lib.RolloutOut)):
+        assert lib.mbe_struct_size(which) == ctypes.sizeof(struct), struct.__name__
+    assert lib.mbe_struct_size(99) == -1
 
 
 def test_library_rejects_bad_configs_without_a_gpu():
