@@ -16,8 +16,10 @@ def make(env_id: str, **kwargs):
         raise KeyError(f"unknown environment id {env_id!r}; known: {sorted(_REGISTRY)}")
     entry, defaults = _REGISTRY[env_id]
     config = {}
-    config.update(defaults.get("config", {}))
     config.update(kwargs.pop("config", {}) or {})
+    # the id fixes the step semantics and the handler (a full MComCore.default_config() passed as
+    # `config`, as in the reference README's customisation example, must not undo them)
+    config.update(defaults.get("config", {}))
     for key in ("num_envs", "device", "autoreset", "env_offset"):
         if key in kwargs:
             config[key] = kwargs.pop(key)

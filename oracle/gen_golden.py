@@ -99,6 +99,78 @@ CASES["two_classes"] = ([(50, 50), (150, 50), (50, 150), (150, 150), (100, 100)]
                         ep_cfg(25, {"ue": {"velocity": 8}}), 25)
 
 
+# ---- the plugin surface: per-UE parameters (entities.py:32-57) and Channel subclasses that override
+# power_loss only (channels.py:18-21; README.md:108-121).  name: (bs_xy, nue, cfg, steps, bs_over, ue_over, channel)
+PLUGIN_CASES = {
+    "two_ue_classes": ([(50, 50), (150, 50), (50, 150), (150, 150)], 10, ep_cfg(30, {"ue": {"velocity": 6}}), 30, None,
+                       {1: {"velocity": 2.5}, 4: {"velocity": 2.5}, 7: {"velocity": 2.5, "snr_tr": 1e-6},
+                        8: {"snr_tr": 1e-6}}, None),
+    "ue_bs_classes": ([(40, 40), (160, 60), (100, 160), (30, 150), (100, 90)], 12, ep_cfg(25, {"ue": {"velocity": 8}}), 25,
+                      {1: {"tx": 30}, 3: {"tx": 30, "bw": 18e6}},
+                      {0: {"noise": 4e-9}, 3: {"height": 2.2, "velocity": 3}, 5: {"noise": 4e-9},
+                       9: {"height": 2.2, "velocity": 3}, 10: {"snr_tr": 5e-8, "velocity": 15}}, None),
+    "pathloss_readme": ([(50, 50), (150, 50), (100, 150)], 9, ep_cfg(25, {"ue": {"velocity": 7}}), 25, None, None,
+                        ("pathloss", 2.0)),
+    "pathloss_short_range": ([(50, 50), (150, 50), (100, 150), (100, 100)], 12,
+                             ep_cfg(30, {"ue": {"velocity": 9, "snr_tr": 1e-3}}), 30, None, None, ("pathloss", 2.6)),
+    "two_slope": ([(60, 60), (140, 60), (60, 140), (140, 140)], 10, ep_cfg(30, {"ue": {"velocity": 8, "snr_tr": 0.1}}), 30,
+                  None, {2: {"snr_tr": 1.0}, 6: {"snr_tr": 1.0}}, ("two_slope", 2.0, 4.5, 25.0)),
+}
+PLUGIN_GYM = {  # GYM-order episodes by the reference's primitives with the same plugins
+    "two_ue_classes": ("two_ue_classes", 21),
+    "two_slope": ("two_slope", 22),
+}
+
+
+def plugin_config(cfg, channel):
+    """cfg + the reference-side channel class / params for a ("name", *args) channel spec."""
+    if channel is None:
+        return cfg
+    cls = rh.custom_channels()[channel[0]]
+    names = {"pathloss": ("gamma",), "two_slope": ("gamma1", "gamma2", "d_break")}[channel[0]]
+    out = dict(cfg)
+    out["channel"] = cls
+    out["channel_params"] = dict(zip(names, channel[1:]))
+    return out
+
+
+def record_plugin_case(bs_xy, nue, cfg, steps, bs_over, ue_over, channel, actions=None):
+    env = rh.make_fixed_layout_env(bs_xy, nue, config=plugin_config(cfg, channel), bs_over=bs_over, ue_over=ue_over)
+    rec = rh.record_fork_episode(env, steps) if actions is None else rh.record_gym_pieces_episode(env, actions)
+    shell = record_case(bs_xy, nue, cfg, 1, bs_over)
+    rec["params"] = shell["params"]
+    if bs_over:
+        rec["bs_over"] = shell["bs_over"]
+    if ue_over:
+        ren = {"velocity": "velocity", "snr_tr": "snr_tr", "noise": "noise", "height": "ue_height"}
+        rec["ue_over"] = [{ren[k]: v for k, v in ue_over.get(i, {}).items()} for i in range(nue)]
+    if channel:
+        rec["params"]["channel"] = list(channel)
+    return rec
+
+
+def plugin_golden():
+    """-> tests/golden/fork_<name>.json and gymref_<name>.json for the plugin-surface cases."""
+    for name, (bs_xy, nue, cfg, steps, bs_over, ue_over, channel) in PLUGIN_CASES.items():
+        rec = record_plugin_case(bs_xy, nue, cfg, steps, bs_over, ue_over, channel)
+        path = os.path.join(OUT, f"fork_{name}.json")
+        with open(path, "w") as f:
+            json.dump(rec, f, separators=(",", ":"))
+        nconn = sum(st["n_connected"] for st in rec["steps"])
+        print(os.path.basename(path), steps, "steps,", nconn, "connected UE-steps,", os.path.getsize(path), "bytes")
+    for name, (case, aseed) in PLUGIN_GYM.items():
+        bs_xy, nue, cfg, steps, bs_over, ue_over, channel = PLUGIN_CASES[case]
+        rng = np.random.default_rng(aseed)
+        actions = [[int(a) for a in rng.integers(0, len(bs_xy) + 1, size=nue)] for _ in range(steps)]
+        rec = record_plugin_case(bs_xy, nue, cfg, steps, bs_over, ue_over, channel, actions)
+        multi = sum(len(c) > 1 for st in rec["steps"] for c in st["conn"])
+        assert multi > 0, "the fixture must exercise UEs connected to several BSs"
+        path = os.path.join(OUT, f"gymref_{name}.json")
+        with open(path, "w") as f:
+            json.dump(rec, f, separators=(",", ":"))
+        print(os.path.basename(path), steps, "steps,", multi, "multi-connection UE-steps,", os.path.getsize(path), "bytes")
+
+
 def random_case(seed):
     """A random scenario (layout, UE count, speed, radio, map, utility curve, sometimes per-BS
     overrides): the generator behind the `rand_*` fixtures and the live cross-check in

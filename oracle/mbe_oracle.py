@@ -63,13 +63,30 @@ class Params:
     util_upper: float = 20.0
     util_coeffs: Sequence[float] = (10.0, 0.0, 10.0)
     scheduler: str = "resource_fair"  # or "proportional_fair" / "rate_fair" (own specs below)
+    # None: OkumuraHata (channels.py:131-146).  Custom Channel subclasses of the reference that only
+    # override power_loss (channels.py:18-21), as the fixtures' generator defines them:
+    #   ("pathloss", gamma)                      the README's example (README.md:108-121)
+    #   ("two_slope", gamma1, gamma2, d_break)   a loss that is NOT affine in log-distance
+    channel: Optional[Sequence] = None
 
 
 # --------------------------------------------------------------------------------------
 # Scalar chain, op-for-op (used for the LUT-free oracle values)
 # --------------------------------------------------------------------------------------
 def power_loss(p: Params, dist: float) -> float:
-    """OkumuraHata.power_loss, reference core/channels.py:132-146."""
+    """OkumuraHata.power_loss, reference core/channels.py:132-146 -- or one of the custom channels
+    (subclasses overriding power_loss only) the fixture generator runs through the reference."""
+    if p.channel is not None:
+        kind = p.channel[0]
+        with np.errstate(divide="ignore"):
+            if kind == "pathloss":  # README.md:108-121: 10 * gamma * log10(4 pi d f)
+                return 10 * p.channel[1] * np.log10(4 * np.pi * dist * p.freq)
+            if kind == "two_slope":  # oracle/gen_golden.py:TwoSlope
+                g1, g2, brk = p.channel[1:4]
+                if dist <= brk:
+                    return 10 * g1 * np.log10(4 * np.pi * dist * p.freq)
+                return 10 * g1 * np.log10(4 * np.pi * brk * p.freq) + 10 * g2 * np.log10(dist / brk)
+        raise ValueError(f"unknown channel {p.channel!r}")
     ch = 0.8 + (1.1 * np.log10(p.freq) - 0.7) * p.ue_height - 1.56 * np.log10(p.freq)
     tmp_1 = 69.55 - ch + 26.16 * np.log10(p.freq) - 13.82 * np.log10(p.bs_height)
     tmp_2 = 44.9 - 6.55 * np.log10(p.bs_height)
@@ -79,7 +96,8 @@ def power_loss(p: Params, dist: float) -> float:
 def snr_of(p: Params, dist: float) -> float:
     """Channel.calculateSNR, reference core/channels.py:24-27."""
     loss = power_loss(p, dist)
-    power = 10 ** ((p.tx - loss) / 10)
+    with np.errstate(over="ignore"):
+        power = 10 ** ((p.tx - loss) / 10)
     return power / p.noise
 
 
@@ -205,6 +223,7 @@ class ScalarEnv:
     num_ues: int
     wp_source: Optional[object] = None
     bs_over: Optional[list] = None  # per-BS overrides of bw / freq / tx / bs_height (entities.py:6-22)
+    ue_over: Optional[list] = None  # per-UE overrides of velocity / snr_tr / noise / ue_height (entities.py:32-57)
     pos: list = field(default_factory=list)
     wp: list = field(default_factory=list)
     wp_count: list = field(default_factory=list)
@@ -226,25 +245,31 @@ class ScalarEnv:
             if self.wp[u] is None:  # movement.py:44-47
                 self.wp[u] = tuple(int(v) for v in self.wp_source(u, self.wp_count[u]))
                 self.wp_count[u] += 1
-            new, arrived = move_one(self.pos[u], self.wp[u], self.p.velocity)
+            new, arrived = move_one(self.pos[u], self.wp[u], self.p_of(None, u).velocity)
             if arrived:
                 self.wp[u] = None
             self.pos[u] = new
 
-    def p_of(self, b) -> Params:
-        """Parameters seen by the link to BS b (the reference keeps bw/freq/tx/height per BS)."""
-        if not self.bs_over or not self.bs_over[b]:
+    def p_of(self, b, u=None) -> Params:
+        """Parameters seen by the link BS b -- UE u (the reference keeps bw/freq/tx/height per BS and
+        velocity/snr_threshold/noise/height per UE, entities.py:6-57)."""
+        over = {}
+        if b is not None and self.bs_over and self.bs_over[b]:
+            over.update(self.bs_over[b])
+        if u is not None and self.ue_over and self.ue_over[u]:
+            over.update(self.ue_over[u])
+        if not over:
             return self.p
         import dataclasses
 
-        return dataclasses.replace(self.p, **self.bs_over[b])
+        return dataclasses.replace(self.p, **over)
 
     def snr(self, b, u):
         bx, by = self.bs_xy[b]
-        return snr_of(self.p_of(b), int_point_dist(bx, by, *self.pos[u]))
+        return snr_of(self.p_of(b, u), int_point_dist(bx, by, *self.pos[u]))
 
     def connectable(self, b, u):  # base.py:212-214
-        return self.snr(b, u) > self.p.snr_tr
+        return self.snr(b, u) > self.p_of(b, u).snr_tr
 
     def _allocate(self, bs_conns):
         """allocateDataRate2User for every BS (base.py:421-435) + user_total_datarates
@@ -252,7 +277,7 @@ class ScalarEnv:
         pair = {}
         for b, ues in enumerate(bs_conns):
             snrs = [self.snr(b, u) for u in ues]
-            max_alloc = [datarate_of(self.p_of(b), s) for s in snrs]
+            max_alloc = [datarate_of(self.p_of(b, u), s) for u, s in zip(ues, snrs)]
             if self.p.scheduler == "proportional_fair":
                 tot = pf_total(max_alloc)
                 rates = [np.float64(r) * np.float64(r) / tot for r in max_alloc]

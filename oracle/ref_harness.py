@@ -95,7 +95,7 @@ def import_reference():
     return base, entities, custom
 
 
-def make_fixed_layout_env(bs_xy, num_ues, config=None, bs_params=None, ue_params=None, bs_over=None):
+def make_fixed_layout_env(bs_xy, num_ues, config=None, bs_params=None, ue_params=None, bs_over=None, ue_over=None):
     """Reference env with a fixed BS list (what MComCustom does at custom.py:40-62,
     minus the unseeded ``random`` BS generator) and JSON dumps disabled."""
     base, entities, _ = import_reference()
@@ -128,8 +128,48 @@ def make_fixed_layout_env(bs_xy, num_ues, config=None, bs_params=None, ue_params
         if bs_over and bs_over.get(i):
             kw.update(bs_over[i])  # keys of BaseStation.__init__: bw, freq, tx, height
         stations.append(entities.BaseStation(i, tuple(xy), **kw))
-    users = [entities.UserEquipment(i, **uep) for i in range(num_ues)]
+    users = []
+    for i in range(num_ues):
+        kw = dict(uep)
+        if ue_over and ue_over.get(i):
+            kw.update(ue_over[i])  # keys of UserEquipment.__init__: velocity, snr_tr, noise, height
+        users.append(entities.UserEquipment(i, **kw))
     return FixedLayoutEnv(stations, users, config or {})
+
+
+def custom_channels():
+    """Channel subclasses of the REFERENCE's Channel that override power_loss only (the reference's
+    plugin contract, channels.py:18-21).  PathLoss is the README's example verbatim (README.md:108-121,
+    with the module path the fork really has); TwoSlope is not affine in log-distance."""
+    import_reference()
+    import numpy as np
+    from mobile_env.core.channels import Channel
+
+    class PathLoss(Channel):
+        def __init__(self, gamma, **kwargs):
+            super().__init__(**kwargs)
+            # path loss exponent
+            self.gamma = gamma
+
+        def power_loss(self, bs, ue):
+            """Computes power loss between BS and UE."""
+            dist = bs.point.distance(ue.point)
+            loss = 10 * self.gamma * np.log10(4 * np.pi * dist * bs.frequency)
+            return loss
+
+    class TwoSlope(Channel):
+        def __init__(self, gamma1, gamma2, d_break, **kwargs):
+            super().__init__(**kwargs)
+            self.gamma1, self.gamma2, self.d_break = gamma1, gamma2, d_break
+
+        def power_loss(self, bs, ue):
+            dist = bs.point.distance(ue.point)
+            if dist <= self.d_break:
+                return 10 * self.gamma1 * np.log10(4 * np.pi * dist * bs.frequency)
+            return (10 * self.gamma1 * np.log10(4 * np.pi * self.d_break * bs.frequency)
+                    + 10 * self.gamma2 * np.log10(dist / self.d_break))
+
+    return {"pathloss": PathLoss, "two_slope": TwoSlope}
 
 
 def record_fork_episode(env, steps, init_pos=None):

@@ -23,6 +23,8 @@ def test_c_fork_step_replays_reference_episodes(name):
     from oracle.c_oracle import CEnvBatch
 
     rec = load_golden(name)
+    if rec.get("ue_over") or rec["params"].get("channel"):
+        pytest.skip("the compiled restatement models OkumuraHata and one UE class; the Python oracle covers this case")
     E, U = 3, len(rec["init_pos"])
     env = CEnvBatch(params_of(rec), rec["bs_xy"], E, U, bs_over=rec.get("bs_over"))
     env.reset(rec["init_pos"])
@@ -47,6 +49,8 @@ def test_c_gym_step_replays_reference_primitive_episodes(name, handler):
     from oracle.c_oracle import CEnvBatch
 
     rec = load_gymref(name)
+    if rec.get("ue_over") or rec["params"].get("channel"):
+        pytest.skip("the compiled restatement models OkumuraHata and one UE class; the Python oracle covers this case")
     E, U, B = 2, len(rec["init_pos"]), len(rec["bs_xy"])
     env = CEnvBatch(params_of(rec), rec["bs_xy"], E, U, handler=handler, bs_over=rec.get("bs_over"))
     env.reset(rec["init_pos"])

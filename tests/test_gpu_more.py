@@ -433,3 +433,72 @@ def test_handle_on_another_device_does_not_change_the_current_device():
     env.step(acts)
     torch.cuda.synchronize(1)
     assert torch.cuda.current_device() == 0
+
+
+def test_readme_pathloss_example_runs_verbatim_and_matches_the_oracle():
+    """The reference README's customisation example (README.md:108-121) against this package's module
+    path: a Channel subclass that overrides power_loss only, passed through config['channel'] /
+    config['channel_params'].  Connection sets, positions and FP64 rates must equal the scalar oracle
+    running the same loss; observations and rewards to 1e-5."""
+    import mobile_env_gan_b200 as gymnasium  # `make` with the Gymnasium ids (gymnasium itself is not a dependency)
+    from mobile_env_gan_b200.core.base import MComCore
+    from mobile_env_gan_b200.core.channel import Channel
+    from oracle import mbe_oracle as orc
+
+    class PathLoss(Channel):
+        def __init__(self, gamma, **kwargs):
+            super().__init__(**kwargs)
+            # path loss exponent
+            self.gamma = gamma
+
+        def power_loss(self, bs, ue):
+            """Computes power loss between BS and UE."""
+            dist = bs.point.distance(ue.point)
+            loss = 10 * self.gamma * np.log10(4 * np.pi * dist * bs.frequency)
+            return loss
+
+    # replace default channel model in configuration
+    config = MComCore.default_config()
+    config['channel'] = PathLoss
+
+    # pass init parameters to custom channel class!
+    config['channel_params'].update({'gamma': 2.0})
+
+    # create environment with custom channel model
+    config.update({"num_envs": 4, "ue": dict(config["ue"], snr_tr=2e-3, velocity=9.0)})  # a range that bites on 200 x 200
+    env = gymnasium.make('mobile-small-central-v0', config=config)
+    # ...
+    assert env.mode == "gym" and env.plan.classes[0]["log2snr_lut"] is None  # affine in log-distance: SFU path
+    E, U, B = 4, env.NUM_USERS, env.NUM_STATIONS
+    rng = np.random.default_rng(8)
+    K = 40
+    wp = rng.integers(0, 200, size=(E, U, K, 2)).astype(np.int16)
+    init = rng.integers(0, 200, size=(E, U, 2)).astype(np.int16)
+    init[0, 0] = env.bs_xy[0].cpu().numpy()  # a UE exactly on a BS: d = 0, log10(0) = -inf, snr = +inf
+    env.reset()
+    env.inject_waypoints(wp)
+    env.set_positions(init)
+    p = orc.Params(velocity=9.0, snr_tr=2e-3, channel=("pathloss", 2.0))
+    bs_xy = env.bs_xy.cpu().tolist()
+    refs = []
+    for e in range(E):
+        r = orc.ScalarEnv(p, bs_xy, U, wp_source=lambda u, k, e=e: wp[e, u, k])
+        r.reset(init[e])
+        refs.append(r)
+    ranged = 0
+    for k in range(20):
+        acts = rng.integers(0, B + 1, size=(E, U)).astype(np.int32)
+        obs, rew, term, trunc, info = env.step(torch.from_numpy(acts).cuda())
+        for e in range(E):
+            o, r, done, inf = refs[e].step_gym(acts[e], "central")
+            want = [sum(1 << b for b in c) for c in ([sorted(c) for c in refs[e].conn])]
+            assert (env.conn[e].cpu().numpy().astype(np.int64) & 0xFFFFFFFF).tolist() == want, (k, e)
+            assert env.pos[e].cpu().tolist() == [list(q) for q in inf["pos"]], (k, e)
+            assert env.rate[e].cpu().tolist() == inf["rate"], (k, e)  # FP64, bit-exact (inf included)
+            close(env.utility_scaled[e].cpu(), inf["utility"], "utility")
+            close(float(rew[e]), r, "reward")
+            got = obs[e].reshape(U, -1).cpu().numpy()
+            fin = np.isfinite(o)  # a UE standing on a BS has snr = inf there: inf/inf in the FP64 spec
+            close(got[fin], o[fin], "observation")
+            ranged += sum(1 for u in range(U) for b in range(B) if not refs[e].connectable(b, u))
+    assert ranged > 0  # the threshold really cut links

@@ -37,6 +37,68 @@ def make_env(bs_xy, nue, config):
     return MComCore(stations, users, config)
 
 
+def plugin_channels():
+    """The channel subclasses of the plugin fixtures, written against THIS package's Channel exactly as
+    oracle/ref_harness.py:custom_channels writes them against the reference's: power_loss only
+    (PathLoss is the reference README's example, README.md:108-121)."""
+    from mobile_env_gan_b200.core.channels import Channel
+
+    class PathLoss(Channel):
+        def __init__(self, gamma, **kwargs):
+            super().__init__(**kwargs)
+            # path loss exponent
+            self.gamma = gamma
+
+        def power_loss(self, bs, ue):
+            """Computes power loss between BS and UE."""
+            dist = bs.point.distance(ue.point)
+            loss = 10 * self.gamma * np.log10(4 * np.pi * dist * bs.frequency)
+            return loss
+
+    class TwoSlope(Channel):
+        def __init__(self, gamma1, gamma2, d_break, **kwargs):
+            super().__init__(**kwargs)
+            self.gamma1, self.gamma2, self.d_break = gamma1, gamma2, d_break
+
+        def power_loss(self, bs, ue):
+            dist = bs.point.distance(ue.point)
+            if dist <= self.d_break:
+                return 10 * self.gamma1 * np.log10(4 * np.pi * dist * bs.frequency)
+            return (10 * self.gamma1 * np.log10(4 * np.pi * self.d_break * bs.frequency)
+                    + 10 * self.gamma2 * np.log10(dist / self.d_break))
+
+    return {"pathloss": (PathLoss, ("gamma",)), "two_slope": (TwoSlope, ("gamma1", "gamma2", "d_break"))}
+
+
+def env_from_record(rec, extra):
+    """The env of a golden record: per-BS / per-UE parameter overrides as the reference's entity
+    objects carry them (entities.py:6-57) and, when recorded, a power_loss-only Channel subclass."""
+    MComCore, BaseStation, UserEquipment = _mods()
+    from mobile_env_gan_b200.core.util import deep_dict_merge
+
+    config = golden_config(rec, extra)
+    chan = rec["params"].get("channel")
+    if chan:
+        cls, names = plugin_channels()[chan[0]]
+        config["channel"] = cls
+        config["channel_params"] = dict(zip(names, chan[1:]))
+    cfg = deep_dict_merge(MComCore.default_config(), config)
+    bs_ren = {"tx": "tx", "bw": "bw", "freq": "freq", "bs_height": "height"}
+    ue_ren = {"velocity": "velocity", "snr_tr": "snr_tr", "noise": "noise", "ue_height": "height"}
+    stations, users = [], []
+    for i, xy in enumerate(rec["bs_xy"]):
+        kw = dict(cfg["bs"])
+        if rec.get("bs_over"):
+            kw.update({bs_ren[k]: v for k, v in rec["bs_over"][i].items()})
+        stations.append(BaseStation(i, tuple(xy), **kw))
+    for i in range(len(rec["init_pos"])):
+        kw = dict(cfg["ue"])
+        if rec.get("ue_over"):
+            kw.update({ue_ren[k]: v for k, v in rec["ue_over"][i].items()})
+        users.append(UserEquipment(i, **kw))
+    return MComCore(stations, users, config)
+
+
 def close(a, b, what=""):
     np.testing.assert_allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64),
                                rtol=RTOL, atol=ATOL, err_msg=what)
@@ -66,22 +128,11 @@ def test_fork_replays_reference_trajectory(name, fast):
     rec = load_golden(name)
     E = 5  # replicas of the same episode: also checks envs are independent of their slot
     U = len(rec["init_pos"])
-    if rec.get("bs_over"):  # per-BS radio parameters, as the reference's BaseStation objects carry them
-        MComCore, BaseStation, UserEquipment = _mods()
-        from mobile_env_gan_b200.core.util import deep_dict_merge
-
-        config = golden_config(rec, {"num_envs": E, "mode": "fork"})
-        cfg = deep_dict_merge(MComCore.default_config(), config)
-        ren = {"tx": "tx", "bw": "bw", "freq": "freq", "bs_height": "height"}
-        stations = []
-        for i, xy in enumerate(rec["bs_xy"]):
-            kw = dict(cfg["bs"])
-            kw.update({ren[k]: v for k, v in rec["bs_over"][i].items()})
-            stations.append(BaseStation(i, tuple(xy), **kw))
-        env = MComCore(stations, [UserEquipment(i, **cfg["ue"]) for i in range(U)], config)
-        assert len(env.plan.classes) > 1
-    else:
-        env = make_env(rec["bs_xy"], U, golden_config(rec, {"num_envs": E, "mode": "fork"}))
+    env = env_from_record(rec, {"num_envs": E, "mode": "fork"})
+    if rec.get("bs_over"):
+        assert env.plan.num_bs_classes > 1
+    if rec.get("ue_over"):
+        assert env.plan.ue_class is not None and len(env.plan.classes) == env.plan.num_bs_classes * len(env.plan.ue_classes)
     wide = U > 32 or len(rec["bs_xy"]) > 32  # block-per-env kernel: no debug SNR output
     if wide and not fast:
         pytest.skip("wide shapes have a single kernel (covered by fast=True)")
@@ -286,22 +337,7 @@ def test_gym_step_replays_reference_primitive_episodes(name, handler):
     positions, done and FP64 rates bit-exact; utilities, reward and the broadcast BS utilities 1e-5."""
     rec = load_gymref(name)
     E, U, B = 5, len(rec["init_pos"]), len(rec["bs_xy"])
-    extra = {"num_envs": E, "mode": "gym", "handler": handler}
-    if rec.get("bs_over"):
-        MComCore, BaseStation, UserEquipment = _mods()
-        from mobile_env_gan_b200.core.util import deep_dict_merge
-
-        config = golden_config(rec, extra)
-        cfg = deep_dict_merge(MComCore.default_config(), config)
-        ren = {"tx": "tx", "bw": "bw", "freq": "freq", "bs_height": "height"}
-        stations = []
-        for i, xy in enumerate(rec["bs_xy"]):
-            kw = dict(cfg["bs"])
-            kw.update({ren[k]: v for k, v in rec["bs_over"][i].items()})
-            stations.append(BaseStation(i, tuple(xy), **kw))
-        env = MComCore(stations, [UserEquipment(i, **cfg["ue"]) for i in range(U)], config)
-    else:
-        env = make_env(rec["bs_xy"], U, golden_config(rec, extra))
+    env = env_from_record(rec, {"num_envs": E, "mode": "gym", "handler": handler})
     seq = golden_waypoints(rec)
     K = max(1, max(len(s) for s in seq))
     wp = np.zeros((E, U, K, 2), dtype=np.int16)

@@ -28,7 +28,7 @@ def run_scalar(rec):
     p = params_of(rec)
     seq = golden_waypoints(rec)
     env = orc.ScalarEnv(p, rec["bs_xy"], len(rec["init_pos"]), wp_source=lambda u, k: seq[u][k],
-                        bs_over=rec.get("bs_over"))
+                        bs_over=rec.get("bs_over"), ue_over=rec.get("ue_over"))
     env.reset(rec["init_pos"])
     return [env.step_fork() for _ in rec["steps"]]
 
@@ -75,7 +75,7 @@ def test_scalar_oracle_gym_step_matches_reference_primitives(name, handler):
     p = params_of(rec)
     seq = golden_waypoints(rec)
     env = orc.ScalarEnv(p, rec["bs_xy"], len(rec["init_pos"]), wp_source=lambda u, k: seq[u][k],
-                        bs_over=rec.get("bs_over"))
+                        bs_over=rec.get("bs_over"), ue_over=rec.get("ue_over"))
     env.reset(rec["init_pos"])
     for k, (acts, g) in enumerate(zip(rec["actions"], rec["steps"])):
         ok = [[env.connectable(b, u) for b in range(len(rec["bs_xy"]))] for u in range(env.num_ues)]
@@ -117,8 +117,8 @@ def test_scalar_oracle_matches_live_reference_on_random_scenarios(seed):
 @pytest.mark.parametrize("name", golden_names())
 def test_batch_oracle_matches_reference(name):
     rec = load_golden(name)
-    if rec.get("bs_over"):
-        pytest.skip("the vectorised oracle models one BS class; the scalar oracle covers this case")
+    if rec.get("bs_over") or rec.get("ue_over") or rec["params"].get("channel"):
+        pytest.skip("the vectorised oracle models one link class and the default channel; the scalar oracle covers this case")
     p = params_of(rec)
     pos = np.array([rec["init_pos"]], dtype=np.int64)
     wp = np.full_like(pos, -1)
