@@ -21,7 +21,7 @@
  * scenario shapes have fused compile-time variants: several UEs per thread for 15 x 4, a thread per
  * env for the fork's 7 UEs x 10 per-env BS slots -- mbe_step_kernel_name() tells which);
  * 32 < U <= 1024 or 32 < B <= 64, and the ProportionalFair / RateFair schedulers, run on the
- * block-per-env kernel (fused mbe_step / mbe_reset only; no mbe_stage / mbe_observe / mbe_step_window).
+ * block-per-env kernel (every entry point; needs width^2 + height^2 < 2^24).
  *
  * Data layout (structure of arrays, env-major; E = envs on this rank, U = UEs, B = BS slots,
  * MW = ceil(B/32), F = 2B+1 (central) or 4B+1 (multi-agent)):

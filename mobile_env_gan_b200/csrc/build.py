@@ -36,7 +36,7 @@ def build(force: bool = False, verbose: bool = False, out: str = None, defines=(
     if out is None and not force and not is_stale():
         return LIB
     cmd = [
-        nvcc_path(), "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+        nvcc_path(), "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-pthread",
         "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
         "--expt-relaxed-constexpr", "--extended-lambda",
         "-Xptxas", "-v" if verbose else "-O3",

@@ -17,6 +17,10 @@
 #include "mbe_step_big.cuh"
 #include "mbe_step_upt.cuh"
 #include "mbe_step_tpe.cuh"
+#include "mbe_host_wire.cuh"
+
+#include <memory>
+#include <sched.h>
 
 namespace {
 
@@ -95,6 +99,12 @@ struct mbe_env {
   // mbe_step_host pipeline: second stream + fork/join events (created on first use)
   cudaStream_t host_stream = nullptr;
   cudaEvent_t host_fork = nullptr, host_join = nullptr;
+  // compact observation wire format of mbe_step_host (mbe_host_wire.cuh; created on first use)
+  mbe::WireShape wire_shape = {};
+  unsigned char* wire_dev = nullptr;     // [E * bytes_per_env]
+  unsigned char* wire_pinned = nullptr;  // the same, pinned host staging
+  std::vector<cudaEvent_t> wire_events;  // one per env window
+  std::unique_ptr<mbe::WorkerPool> wire_pool;
 };
 
 namespace {
@@ -121,6 +131,7 @@ struct SpecEntry {
   size_t smem;
   void (*pipe_fn)(mbe::StepArgs);  // persistent, TMA-pipelined variant (E % EPB == 0)
   size_t pipe_smem;
+  void (*mc_fn)(mbe::StepArgs);    // several BS classes in a shared layout (nullptr for per-env layouts)
 };
 
 #define MBE_SPEC(MODE, HANDLER, U, B, PE)                                             \
@@ -128,7 +139,8 @@ struct SpecEntry {
     MODE, HANDLER, U, B, PE, mbe::step_spec_kernel<MODE, HANDLER, U, B, (PE != 0)>,   \
         mbe::spec_smem_bytes<HANDLER, U, B, (PE != 0)>(MODE == 1),                    \
         mbe::step_pipe_kernel<MODE, HANDLER, U, B, (PE != 0)>,                        \
-        mbe::pipe_smem_bytes<HANDLER, U, B, (PE != 0)>(MODE == 1)                     \
+        mbe::pipe_smem_bytes<HANDLER, U, B, (PE != 0)>(MODE == 1),                    \
+        mbe::spec_mc_kernel<MODE, HANDLER, U, B, (PE != 0)>()                         \
   }
 
 // shapes with a compile-time specialisation: the scenario sizes of BASELINE.json (small 3x5,
@@ -388,9 +400,10 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
     for (const SpecEntry& sp : kSpecs)
       if (sp.mode == cfg->mode && (sp.handler == cfg->handler || !gym) && sp.U == a.U && sp.B == a.B &&
           sp.per_env == a.bs_per_env) {
-        env->spec = sp.fn;
+        if (cfg->num_classes > 1 && !sp.mc_fn) break;  // per-env layouts have one class: generic kernel
+        env->spec = cfg->num_classes > 1 ? sp.mc_fn : sp.fn;
         env->spec_smem = sp.smem;
-        if (a.E % a.epb == 0) {
+        if (a.E % a.epb == 0 && cfg->num_classes == 1) {
           env->pipe = sp.pipe_fn;
           env->pipe_smem = sp.pipe_smem;
         }
@@ -420,6 +433,12 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
       env->tpe_rollout = mbe::step_tpe_fork_kernel<7, 10, true>;
       env->tpe_rollout_smem = sizeof(mbe::TpeRolloutSmem<7, 10>);
     }
+  }
+  if (env->big && std::floor(cfg->width) * std::floor(cfg->width) + std::floor(cfg->height) * std::floor(cfg->height) >=
+                      16777216.0) {
+    mbe_destroy(env);
+    return fail("mbe_create: the block-per-env kernel (wide shapes, ProportionalFair / RateFair) needs a map whose "
+                "squared diagonal is below 2^24 (distances are exact FP32 integers)");
   }
   env->smem = env->big ? 0 : mbe::smem_bytes(gym, ma, a.epb, a.U, a.B, a.F, a.bs_per_env);
   env->grid = env->big ? a.E : (a.E + a.epb - 1) / a.epb;
@@ -493,6 +512,10 @@ void mbe_destroy(mbe_env* env) {
   if (env->host_stream) cudaStreamDestroy(env->host_stream);
   if (env->host_fork) cudaEventDestroy(env->host_fork);
   if (env->host_join) cudaEventDestroy(env->host_join);
+  env->wire_pool.reset();
+  for (cudaEvent_t e : env->wire_events) cudaEventDestroy(e);
+  if (env->wire_dev) cudaFree(env->wire_dev);
+  if (env->wire_pinned) cudaFreeHost(env->wire_pinned);
   delete env;
 }
 
@@ -604,9 +627,6 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool gym = env->cfg.mode == MBE_MODE_GYM, ma = env->cfg.handler == MBE_HANDLER_MA;
   if (env->big) {
-    if (op == mbe::OP_OBSERVE || (op == mbe::OP_STEP && phases != MBE_PHASE_ALL))
-      return fail("split phases / observe are not available on the block-per-env kernel (wide shapes)");
-    if (a.dbg_snr) return fail("the debug SNR output is not available for wide shapes");
     if (!gym)
       mbe::step_big_kernel<0, 0><<<grid, mbe::kBigThreads, sizeof(mbe::BigSmem), st>>>(a);
     else if (!ma)
@@ -688,7 +708,6 @@ int mbe_step(mbe_env* env, void* stream) { return launch(env, mbe::OP_STEP, MBE_
 
 int mbe_step_window(mbe_env* env, int first_env, int num_envs, void* stream) {
   if (!env) return fail("null handle");
-  if (env->big) return fail("mbe_step_window: not available on the block-per-env kernel (wide shapes)");
   if (first_env < 0 || num_envs <= 0 || (long long)first_env + num_envs > env->cfg.num_envs)
     return fail("mbe_step_window: window [%d, +%d) outside 0..%d", first_env, num_envs, env->cfg.num_envs);
   if (first_env % 32) return fail("mbe_step_window: first_env must be a multiple of 32 (16-byte aligned slices)");
@@ -805,14 +824,38 @@ int mbe_step_host(mbe_env* env, const int32_t* actions_host, float* obs_host, fl
   if (!gym && (actions_host || obs_host || reward_host))
     return fail("mbe_step_host: actions, obs and reward only exist in GYM mode");
   // Env windows on two streams: the action upload and the step of window c+1 overlap the result
-  // download of window c (PCIe is full duplex).  Measured on B200 (profiles/README.md): the call is
-  // bound by the observation download (~48 GB/s); 4 windows gain 2% there and cost 13% when no
-  // observations are downloaded -> default 4 with obs_host, 1 without; MBE_HOST_WINDOWS overrides.
+  // download of window c (PCIe is full duplex).  With observations the call is bound by their
+  // download; they cross PCIe in the compact wire format (mbe_host_wire.cuh) and host threads expand
+  // window c into obs_host while window c+1 is still arriving (MBE_HOST_WIRE=raw: plain FP32 rows by
+  // DMA, no host threads).  MBE_HOST_WINDOWS / MBE_HOST_THREADS override the defaults.
+  const char* wire_v = std::getenv("MBE_HOST_WIRE");
+  const bool compact = obs_host != nullptr && !(wire_v && std::strcmp(wire_v, "raw") == 0);
   const char* wv = std::getenv("MBE_HOST_WINDOWS");
-  const int want = wv ? std::max(1, std::atoi(wv)) : (obs_host ? 4 : 1);
+  const int want = wv ? std::max(1, std::atoi(wv)) : (obs_host ? (compact ? 8 : 4) : 1);
   constexpr int kAlign = 384;  // multiple of every kernel's envs-per-CTA and of 32 (16-byte aligned slices)
-  int windows = env->big ? 1 : std::min(want, std::max(1, a.E / (8 * kAlign)));
+  int windows = std::min(want, std::max(1, a.E / (env->big ? kAlign : 8 * kAlign)));
   const int per = ((a.E + windows - 1) / windows + kAlign - 1) / kAlign * kAlign;
+  windows = (a.E + per - 1) / per;
+  if (compact && !env->wire_dev) {
+    mbe::WireShape& w = env->wire_shape;
+    w.U = a.U, w.B = a.B, w.F = a.F, w.MW = (a.B + 31) >> 5, w.ma = ma ? 1 : 0;
+    w.W = w.MW * (ma ? 2 : 1);
+    const size_t bytes = (size_t)a.E * w.bytes_per_env();
+    MBE_CUDA(cudaMalloc(&env->wire_dev, bytes));
+    MBE_CUDA(cudaMemset(env->wire_dev, 0, bytes));
+    MBE_CUDA(cudaHostAlloc(&env->wire_pinned, bytes, cudaHostAllocDefault));
+    const char* tv = std::getenv("MBE_HOST_THREADS");
+    cpu_set_t set;
+    int cpus = (sched_getaffinity(0, sizeof set, &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+    const int threads = tv ? std::max(1, std::atoi(tv)) : std::max(1, std::min(cpus, 32));
+    env->wire_pool.reset(new mbe::WorkerPool(threads - 1));  // the calling thread is the last worker
+  }
+  if (compact)
+    while ((int)env->wire_events.size() < windows) {
+      cudaEvent_t e;
+      MBE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      env->wire_events.push_back(e);
+    }
   if (windows > 1 && !env->host_stream) {
     MBE_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
     MBE_CUDA(cudaEventCreateWithFlags(&env->host_fork, cudaEventDisableTiming));
@@ -833,18 +876,44 @@ int mbe_step_host(mbe_env* env, const int32_t* actions_host, float* obs_host, fl
     if (int rc = (windows > 1 ? launch(env, mbe::OP_STEP, MBE_PHASE_ALL, nullptr, s, (size_t)first, count)
                               : launch(env, mbe::OP_STEP, MBE_PHASE_ALL, nullptr, s)))
       return rc;
-    if (obs_host)
+    if (compact) {
+      const mbe::WireShape& ws = env->wire_shape;
+      const size_t off = (size_t)first * ws.bytes_per_env(), len = (size_t)count * ws.bytes_per_env();
+      const int rows = count * a.U;
+      mbe::wire_pack_kernel<<<(rows + 255) / 256, 256, 0, s>>>(env->bufs.obs, env->wire_dev + off, first, count, ws);
+      MBE_CUDA(cudaGetLastError());
+      MBE_CUDA(cudaMemcpyAsync(env->wire_pinned + off, env->wire_dev + off, len, cudaMemcpyDeviceToHost, s));
+    } else if (obs_host) {
       MBE_CUDA(cudaMemcpyAsync(obs_host + fu * a.F, env->bufs.obs + fu * a.F, cu * a.F * 4, cudaMemcpyDeviceToHost, s));
+    }
     if (reward_host) {
       const size_t f = ma ? fu : (size_t)first, c = ma ? cu : (size_t)count;
       MBE_CUDA(cudaMemcpyAsync(reward_host + f, env->bufs.reward + f, c * 4, cudaMemcpyDeviceToHost, s));
     }
     if (done_host)
       MBE_CUDA(cudaMemcpyAsync(done_host + first, env->bufs.done + first, (size_t)count, cudaMemcpyDeviceToHost, s));
+    if (compact) MBE_CUDA(cudaEventRecord(env->wire_events[w], s));
   }
   if (windows > 1) {
     MBE_CUDA(cudaEventRecord(env->host_join, env->host_stream));
     MBE_CUDA(cudaStreamWaitEvent(st, env->host_join, 0));
+  }
+  if (compact) {
+    // expand window after window as it lands; the pool works on window c while window c+1 is in flight
+    mbe::WorkerPool* pool = env->wire_pool.get();
+    const mbe::WireShape ws = env->wire_shape;
+    const int chunks = std::max(1, 4 * (pool->size() + 1));
+    for (int w = 0, first = 0; first < a.E; ++w, first += per) {
+      const int count = std::min(per, a.E - first);
+      MBE_CUDA(cudaEventSynchronize(env->wire_events[w]));
+      const unsigned char* src = env->wire_pinned + (size_t)first * ws.bytes_per_env();
+      float* dst = obs_host + (size_t)first * a.U * a.F;
+      pool->submit(chunks, [=](int c) {
+        const int lo = (int)((long long)count * c / chunks), hi = (int)((long long)count * (c + 1) / chunks);
+        if (hi > lo) mbe::wire_expand_any(src, dst, count, lo, hi, ws);
+      });
+    }
+    pool->wait();
   }
   MBE_CUDA(cudaStreamSynchronize(st));
   return 0;

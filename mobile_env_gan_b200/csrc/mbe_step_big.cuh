@@ -1,32 +1,50 @@
 // Block-per-env fused step kernel for the wide shapes (32 < U <= 1024 UEs or 32 < B <= 64 BS
-// slots, e.g. the synthetic 64 x 512 scale-up): one CTA of 256 threads owns one env, every thread
-// keeps up to 4 UEs in registers, the BS table and the per-BS accumulators live in shared memory.
-// Per-BS counts / proportional-fair totals / multi-agent BS utilities are integer (fixed-point)
-// shared-memory atomics, so every result is independent of the order threads arrive in.
+// slots, e.g. the synthetic 64 x 512 scale-up) and for the ProportionalFair / RateFair schedulers:
+// one CTA of 256 threads owns one env.
+//
+// Two mappings inside the CTA:
+//   * per-UE work (movement, connectivity, association / action, split, utility): a thread owns up
+//     to 4 UEs in registers, the BS table and the per-BS accumulators live in shared memory.  Per-BS
+//     counts / proportional-fair totals / multi-agent BS utilities are integer (fixed-point)
+//     shared-memory atomics, so every result is independent of the order threads arrive in;
+//   * the observation writer is ROW-PARALLEL: a warp walks its share of the UE rows and its lanes
+//     are the BS columns (lane = b and b + 32, coordinates and per-BS values in registers), so the
+//     row maximum of log2 snr is one warp reduction (redux.sync.max.f32) and every store instruction
+//     writes 128 contiguous bytes of one observation row straight from registers -- no staging tile,
+//     no transposition.  (Round 1 produced lane-per-row tiles in shared memory and transposed them:
+//     three passes over a padded tile, 2x the instructions; profiles/README.md.)
 // Same arithmetic helpers as the warp-segment kernels (mbe_device.cuh).
 #pragma once
 #include "mbe_device.cuh"
 
+#ifndef MBE_BIG_MIN_BLOCKS
+#define MBE_BIG_MIN_BLOCKS 3
+#endif
+
 namespace mbe {
 
 constexpr int kBigThreads = 256;
+constexpr int kBigWarps = kBigThreads / 32;
 constexpr int kBigMaxI = 4;     // UEs per thread  => U <= 1024
+constexpr int kBigMaxU = kBigMaxI * kBigThreads;
 constexpr int kBigMaxB = 64;    // BS slots        => two 32-bit mask words
 
 struct BigSmem {
-  uint32_t bs[kBigMaxB];
+  float2 bsf[kBigMaxB];  // BS coordinates as floats (integers, exact)
   int cnt[kBigMaxB];
   unsigned long long pf_tot[kBigMaxB];
   long long bsu_acc[kBigMaxB];
   float bsu[kBigMaxB];
   uint8_t cls[kBigMaxB];
-  float red_f[3][kBigThreads / 32];
-  int red_i[2][kBigThreads / 32];
+  float red_f[3][kBigWarps];
+  int red_i[2][kBigWarps];
   float usum, rsum;
   int csum, ncon;
-  // per-warp rows of the observation writer: first the log2(snr) of every BS (one pass), then
-  // reused as the transpose tile of the other feature segments (odd stride: conflict-free)
-  float rows[kBigThreads / 32][32][kBigMaxB + 1];
+  // inputs of the observation rows, published by the threads that own the UEs
+  float2 pxy[kBigMaxU];   // position after the move
+  uint2 cw[kBigMaxU];     // connection mask words
+  float ut[kBigMaxU];     // own-utility column
+  uint8_t ucls[kBigMaxU]; // UE class
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -38,6 +56,12 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(kFull, v, off);
   return v;
+}
+// warp-wide float maximum in one instruction (sm_100a: CREDUX.MAX.F32)
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
 }
 
 // one link's share of its BS (schedules.py:20-22 / proportional fair), rounded like base.py:435
@@ -58,7 +82,7 @@ __device__ __forceinline__ double link_share(const StepArgs& a, const ClassDev& 
 }
 
 template <int MODE, int HANDLER>
-__global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kBigThreads, MBE_BIG_MIN_BLOCKS) step_big_kernel(const __grid_constant__ StepArgs a) {
   constexpr bool GYM = (MODE == 1);
   constexpr bool MA = (HANDLER == 1);
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -68,28 +92,32 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
   const int env = blockIdx.x;
   const unsigned gid = a.env_offset + (unsigned)env;
   const int op = a.op;
+  int ph = a.phases;
+  if (op == OP_RESET || op == OP_OBSERVE) ph = GYM ? 8 : 0;
+  // the env's outputs are (re)written by this launch (per env = per CTA: uniform)
+  if (op == OP_RESET && a.reset_mask != nullptr && a.reset_mask[env] == 0) return;
 
   // ---- P0: env scalars, BS table, accumulators ----
   int t_e = a.t[env], epi = a.episode[env];
   int nb = a.nbs ? a.nbs[env] : B;
   if (tid < B) {
-    s.bs[tid] = a.bs_per_env ? a.bs_xy[(size_t)env * B + tid] : a.bs_xy[tid];
+    int bx, by;
+    unpack_xy(a.bs_per_env ? a.bs_xy[(size_t)env * B + tid] : a.bs_xy[tid], bx, by);
+    s.bsf[tid] = make_float2((float)bx, (float)by);
     s.cls[tid] = a.bs_class ? a.bs_class[tid] : (uint8_t)0;
     s.cnt[tid] = 0;
     s.pf_tot[tid] = 0ull;
     s.bsu_acc[tid] = 0ll;
     s.bsu[tid] = -1.0f;
   }
-  bool touched = true;
-  if (op == OP_RESET) touched = (a.reset_mask == nullptr) || (a.reset_mask[env] != 0);
   __syncthreads();
 
   // ---- per-UE registers ----
   int x[kBigMaxI], y[kBigMaxI], wx[kBigMaxI], wy[kBigMaxI];
   uint32_t c0[kBigMaxI], c1[kBigMaxI], e0[kBigMaxI], e1[kBigMaxI];
   float util[kBigMaxI];
-  double rate[kBigMaxI];
-  int best[kBigMaxI], bestd2[kBigMaxI];
+  int best[kBigMaxI];
+  int ucls[kBigMaxI];
 #pragma unroll
   for (int i = 0; i < kBigMaxI; ++i) {
     const int u = tid + i * kBigThreads;
@@ -97,9 +125,8 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
     wx[i] = wy[i] = -1;
     c0[i] = c1[i] = e0[i] = e1[i] = 0;
     util[i] = -1.0f;
-    rate[i] = 0.0;
     best[i] = -1;
-    bestd2[i] = 0x7fffffff;
+    ucls[i] = 0;
     if (u < U) {
       const size_t idx = (size_t)env * U + u;
       unpack_xy(a.pos[idx], x[i], y[i]);
@@ -108,27 +135,24 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
         c0[i] = a.conn[idx * MW];
         if (MW > 1) c1[i] = a.conn[idx * MW + 1];
       }
+      // link class of (b, this UE) = bs_class[b] * n_ue_classes + ue_class[u] (entities.py:6-57)
+      if (a.ue_class) ucls[i] = (int)a.ue_class[u];
     }
   }
-  bool done = false, fresh = false;
+  bool done = false, fresh = false, util_known = false;
   const bool one_class = a.n_classes == 1 && a.n_ue_classes == 1;
-  const int d2max0 = a.cls[0].d2max;
-  // link class of (b, UE i of this thread) = bs_class[b] * n_ue_classes + ue_class[u] (entities.py:6-57)
-  int ucls[kBigMaxI];
-#pragma unroll
-  for (int i = 0; i < kBigMaxI; ++i) {
-    const int u = tid + i * kBigThreads;
-    ucls[i] = (a.ue_class && u < U) ? (int)a.ue_class[u] : 0;
-  }
   const int nuc = a.n_ue_classes;
   auto link = [&](int i, int b) -> const ClassDev& { return a.cls[(int)s.cls[b] * nuc + ucls[i]]; };
+  const float d2max0f = (float)a.cls[0].d2max;  // exact: below 2^24
 
-  auto d2_to = [&](int i, int b) {
-    int bx, by;
-    unpack_xy(s.bs[b], bx, by);
-    int dx = x[i] - bx, dy = y[i] - by;
-    return dx * dx + dy * dy;
+  // squared distance UE -- BS b in FP32: coordinates are integers below 2^15, so every product and
+  // the sum are exact (whenever the map's squared diagonal is below 2^24; mbe_create checks it)
+  auto d2f_to = [&](float xf, float yf, int b) {
+    const float2 q = s.bsf[b];
+    const float dx = xf - q.x, dy = yf - q.y;
+    return fmaf(dx, dx, dy * dy);
   };
+  auto d2_to = [&](int i, int b) { return (int)d2f_to((float)x[i], (float)y[i], b); };
   auto has_bit = [&](uint32_t lo, uint32_t hi, int b) { return (((b < 32) ? (lo >> b) : (hi >> (b - 32))) & 1u) != 0; };
 
   auto phase_move = [&]() {
@@ -157,7 +181,7 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
     if (tid == 0) {
       float su = 0.0f, sr = 0.0f;
       int sc = 0, sn = 0;
-      for (int w = 0; w < kBigThreads / 32; ++w) {
+      for (int w = 0; w < kBigWarps; ++w) {
         su += s.red_f[0][w];
         sr += s.red_f[1][w];
         sc += s.red_i[0][w];
@@ -168,6 +192,30 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
       s.csum = sc;
       s.ncon = sn;
     }
+    __syncthreads();
+  };
+
+  // allStationUtilities (base.py:438-447) from the connection masks and utilities in registers:
+  // 2^-32 fixed-point sums, so the mean does not depend on the order the threads arrive in
+  auto bs_utilities = [&]() {
+#pragma unroll
+    for (int i = 0; i < kBigMaxI; ++i) {
+      const int u = tid + i * kBigThreads;
+      if (u >= U) continue;
+      const long long q = __double2ll_rn((double)util[i] * 4294967296.0);
+      for (int w = 0; w < 2; ++w) {
+        uint32_t m = w ? c1[i] : c0[i];
+        while (m) {
+          const int b = (__ffs(m) - 1) + 32 * w;
+          m &= m - 1;
+          atomicAdd((unsigned long long*)&s.bsu_acc[b], (unsigned long long)q);
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < B)
+      s.bsu[tid] = s.cnt[tid] ? (float)(__ll2double_rn(s.bsu_acc[tid]) * (1.0 / 4294967296.0) / (double)s.cnt[tid])
+                              : -1.0f;
     __syncthreads();
   };
 
@@ -182,9 +230,8 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
       if (tid < B) {
         int bx = 0, by = 0;
         if (tid < nb) philox_point(a, gid, (unsigned)tid, 0u, P_BSLAYOUT, (unsigned)epi, bx, by);
-        uint32_t p = pack_xy(bx, by);
-        s.bs[tid] = p;
-        a.bs_xy[(size_t)env * B + tid] = p;
+        s.bsf[tid] = make_float2((float)bx, (float)by);
+        a.bs_xy[(size_t)env * B + tid] = pack_xy(bx, by);
       }
       if (tid == 0 && a.nbs) a.nbs[env] = nb;
     }
@@ -205,44 +252,25 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
     __syncthreads();
   };
 
-  if (op == OP_RESET) {
-    if (touched) {
-      reinit_all();
-#pragma unroll
-      for (int i = 0; i < kBigMaxI; ++i) {
-        const int u = tid + i * kBigThreads;
-        if (u >= U) continue;
-        const size_t idx = (size_t)env * U + u;
-        a.utility[idx] = -1.0f;
-        if (a.rate) a.rate[idx] = 0.0;
-        if (!GYM) a.assoc[idx] = -1;
-        if (GYM && MA) a.reward[idx] = 0.0f;
-      }
-      if (tid == 0) {
-        a.done[env] = 0;
-        if (GYM && !MA) a.reward[env] = 0.0f;
-      }
-    }
-  } else {
-    // ================= one step =================
-    if (!GYM) phase_move();  // FORK moves first (base.py:232-233)
-
-    // ---- P1: connectivity, association / action, per-BS accumulators ----
+  // ---- PRE: connectivity, association / action, per-BS accumulators, split, utility ----
+  auto phase_pre = [&]() {
 #pragma unroll
     for (int i = 0; i < kBigMaxI; ++i) {
       const int u = tid + i * kBigThreads;
       if (u >= U) continue;
       const size_t idx = (size_t)env * U + u;
+      const float xf = (float)x[i], yf = (float)y[i];
+      float bestf = 3.0e38f;
       for (int w = 0; w < 2; ++w) {  // one 32-bit mask word at a time (no per-BS word select)
         uint32_t ew = 0;
         const int b_lo = 32 * w, b_hi = min(nb, 32 * w + 32);
         for (int b = b_lo; b < b_hi; ++b) {
-          const int d2 = d2_to(i, b);
-          if (d2 <= (one_class ? d2max0 : link(i, b).d2max)) {  // check_connectivity (base.py:212-214)
+          const float d2f = d2f_to(xf, yf, b);
+          if (d2f <= (one_class ? d2max0f : (float)link(i, b).d2max)) {  // check_connectivity (base.py:212-214)
             ew |= 1u << (b - b_lo);
-            if (!GYM && d2 < bestd2[i]) {  // nearest connectable BS, first minimum (base.py:240)
+            if (!GYM && d2f < bestf) {  // nearest connectable BS, first minimum (base.py:240)
               best[i] = b;
-              bestd2[i] = d2;
+              bestf = d2f;
             }
           }
         }
@@ -259,8 +287,11 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
           const uint32_t bit = 1u << (b & 31);
           cw = (cw & bit) ? (cw & ~bit) : (cw | (ew & bit));
         }
-      } else if (best[i] >= 0) {
-        if (best[i] < 32) c0[i] = 1u << best[i]; else c1[i] = 1u << (best[i] - 32);
+      } else {
+        c0[i] = c1[i] = 0;
+        if (best[i] >= 0) {
+          if (best[i] < 32) c0[i] = 1u << best[i]; else c1[i] = 1u << (best[i] - 32);
+        }
       }
       for (int w = 0; w < 2; ++w) {
         uint32_t m = w ? c1[i] : c0[i];
@@ -277,10 +308,13 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
           }
         }
       }
+      if (a.dbg_snr)
+        for (int b = 0; b < B; ++b)
+          a.dbg_snr[idx * B + b] = (b < nb) ? ex2_sfu(log2_snr(link(i, b), d2_to(i, b))) : 0.0f;
     }
     __syncthreads();
 
-    // ---- P2: split, rounding, utility (base.py:421-435, 413-418, 253-258) ----
+    // split, rounding, utility (base.py:421-435, 413-418, 253-258)
     float fu = 0.0f, fr = 0.0f;
     int ic = 0, in = 0;
 #pragma unroll
@@ -297,7 +331,6 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
           r += link_share(a, link(i, b), d2_to(i, b), s.cnt[b], s.pf_tot[b]);
         }
       }
-      rate[i] = r;
       util[i] = scaled_utility(a, r);
       if (a.rate) a.rate[idx] = r;
       a.utility[idx] = util[i];
@@ -306,24 +339,11 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
       fr += (float)r;
       ic += __popc(c0[i]) + __popc(c1[i]);
       in += (c0[i] | c1[i]) ? 1 : 0;
-      if (GYM && MA) {
-        const long long q = __double2ll_rn((double)util[i] * 4294967296.0);
-        for (int w = 0; w < 2; ++w) {
-          uint32_t m = w ? c1[i] : c0[i];
-          while (m) {
-            const int b = (__ffs(m) - 1) + 32 * w;
-            m &= m - 1;
-            atomicAdd((unsigned long long*)&s.bsu_acc[b], (unsigned long long)q);
-          }
-        }
-      }
     }
+    util_known = true;
     block_sums(fu, fr, ic, in);
     if (GYM && MA) {
-      if (tid < B)  // allStationUtilities (base.py:438-447)
-        s.bsu[tid] = s.cnt[tid] ? (float)(__ll2double_rn(s.bsu_acc[tid]) * (1.0 / 4294967296.0) / (double)s.cnt[tid])
-                                : -1.0f;
-      __syncthreads();
+      bs_utilities();
 #pragma unroll
       for (int i = 0; i < kBigMaxI; ++i) {
         const int u = tid + i * kBigThreads;
@@ -346,10 +366,10 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
             make_float4((float)s.csum, nc, s.usum * a.inv_U, mean_or_zero(s.rsum, nc));
       }
     }
+  };
 
-    if (GYM) phase_move();
-
-    // ---- CLOCK (base.py:280-291, 407-409) ----
+  // ---- CLOCK (base.py:280-291, 407-409) ----
+  auto phase_clock = [&]() {
     t_e += 1;
     done = t_e >= a.ep_time;
     if (tid == 0) a.done[env] = done ? 1 : 0;
@@ -364,86 +384,167 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
       if (a.autoreset) reinit_all();
       else __syncthreads();
     }
-  }
+  };
 
-  // ---- POST: observation rows (GYM) ----
-  // A lane owns one UE row of F floats; the rows of the warp's 32 UEs are contiguous in HBM.  Each
-  // feature segment (connections | snr ratios | utility | broadcast utilities | broadcast counts)
-  // is produced 32 columns at a time into a padded shared tile and written back transposed, so a
-  // store instruction covers 128 contiguous bytes of one row.  log2(snr) is evaluated once per
-  // pair and parked in shared memory until the row maximum is known.
-  if (GYM && touched) {
-    float (*tile)[kBigMaxB + 1] = s.rows[warp];
+  // ---- POST: observation rows (GYM), row-parallel: warp = row, lanes = BS columns ----
+  auto phase_post = [&]() {
+    if (!GYM) return;
+    if (!(ph & 4)) done = !fresh && (t_e >= a.ep_time);  // CLOCK ran in an earlier launch: the clock tells
+    const bool is_fresh = fresh || (t_e == 0);
+    if (!util_known) {
 #pragma unroll
-    for (int i = 0; i < kBigMaxI; ++i) {
-      const int u0 = warp * 32 + i * kBigThreads;  // first UE of this warp's row group
-      if (u0 >= U) continue;                        // warp-uniform
-      const bool active = (u0 + lane < U) && !(done && !fresh);
-      float* gbase = a.obs + ((size_t)env * U + u0) * F;
-      const int nrows = min(32, U - u0);
-      // transposed write-back of tile columns [c0, c0 + n) to feature columns [f0, f0 + n)
-      // (full 32-row tiles of the BASELINE synthetic shape, F = 129 / 257, unroll completely with the
-      // row stride as an immediate: one shared load + one store per row, no address arithmetic)
-      auto flush = [&](int f0, int c0_, int n) {
-        __syncwarp();
-        if (lane < n) {
-          float* g = gbase + f0 + lane;
-          const float* t = &tile[0][c0_ + lane];
-          if (nrows == 32 && F == 129) {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) g[r * 129] = t[r * (kBigMaxB + 1)];
-          } else if (nrows == 32 && F == 257) {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) g[r * 257] = t[r * (kBigMaxB + 1)];
-          } else {
-#pragma unroll 8
-            for (int r = 0; r < nrows; ++r) g[(size_t)r * F] = t[r * (kBigMaxB + 1)];
-          }
-        }
-        __syncwarp();
-      };
-      // pass over the BSs: log2 snr, its maximum, connectable mask, MA count total
-      float lmax = -INFINITY, tot = 0.0f;
-      uint32_t k0 = 0, k1 = 0;
-      if (active)
-        for (int b = 0; b < nb; ++b) {
-          const ClassDev& c = link(i, b);
-          const int d2 = d2_to(i, b);
-          const float l = log2_snr_obs(c, d2);
-          tile[lane][b] = l;
-          lmax = fmaxf(lmax, l);
-          if (d2 <= c.d2max) {
-            if (b < 32) k0 |= 1u << b; else k1 |= 1u << (b - 32);
-            tot += (float)s.cnt[b];
-          }
-        }
-      const float inv_tot = 1.0f / fmaxf(1.0f, tot);
-      // (2) snr / max snr, in place over the parked log2 values
-      for (int b = 0; b < B; ++b) tile[lane][b] = (active && b < nb) ? ex2_sfu(tile[lane][b] - lmax) : 0.0f;
-      for (int b0 = 0; b0 < B; b0 += 32) flush(B + b0, b0, min(32, B - b0));
-      // (1) connection one-hot
-      {
-        const uint32_t m0 = active ? c0[i] : 0u, m1 = active ? c1[i] : 0u;
-        for (int b = 0; b < min(B, 32); ++b) tile[lane][b] = ((m0 >> b) & 1u) ? 1.0f : 0.0f;
-        for (int b = 32; b < B; ++b) tile[lane][b] = ((m1 >> (b - 32)) & 1u) ? 1.0f : 0.0f;
+      for (int i = 0; i < kBigMaxI; ++i) {
+        const int u = tid + i * kBigThreads;
+        if (u < U) util[i] = a.utility[(size_t)env * U + u];
       }
-      for (int b0 = 0; b0 < B; b0 += 32) flush(b0, b0, min(32, B - b0));
-      tile[lane][0] = active ? ((fresh || t_e == 0) ? -1.0f : util[i]) : 0.0f;  // (3) own utility
-      flush(2 * B, 0, 1);
-      if (MA) {
-        // (4) broadcast BS utilities
-        for (int b = 0; b < B; ++b) tile[lane][b] = active ? (has_bit(k0, k1, b) ? s.bsu[b] : -1.0f) : 0.0f;
-        for (int b0 = 0; b0 < B; b0 += 32) flush(2 * B + 1 + b0, b0, min(32, B - b0));
-        // (5) broadcast connection counts, normalised
-        for (int b = 0; b < B; ++b)
-          tile[lane][b] = (active && has_bit(k0, k1, b)) ? (float)s.cnt[b] * inv_tot : 0.0f;
-        for (int b0 = 0; b0 < B; b0 += 32) flush(3 * B + 1 + b0, b0, min(32, B - b0));
+      if (MA && !is_fresh && !done) {  // split phases / mbe_observe: rebuild the per-BS statistics
+        __syncthreads();
+        if (tid < B) {
+          s.cnt[tid] = 0;
+          s.bsu_acc[tid] = 0ll;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kBigMaxI; ++i) {
+          if (tid + i * kBigThreads >= U) continue;
+          for (int w = 0; w < 2; ++w) {
+            uint32_t m = w ? c1[i] : c0[i];
+            while (m) {
+              atomicAdd(&s.cnt[(__ffs(m) - 1) + 32 * w], 1);
+              m &= m - 1;
+            }
+          }
+        }
+        __syncthreads();
+        bs_utilities();
       }
     }
+    if (MA && (is_fresh || done)) {  // nobody is connected in a fresh / finished episode
+      __syncthreads();
+      if (tid < B) {
+        s.cnt[tid] = 0;
+        s.bsu[tid] = -1.0f;
+      }
+    }
+    // publish what the rows need
+#pragma unroll
+    for (int i = 0; i < kBigMaxI; ++i) {
+      const int u = tid + i * kBigThreads;
+      if (u >= U) continue;
+      s.pxy[u] = make_float2((float)x[i], (float)y[i]);
+      s.cw[u] = (is_fresh || done) ? make_uint2(0u, 0u) : make_uint2(c0[i], c1[i]);
+      s.ut[u] = is_fresh ? -1.0f : util[i];
+      s.ucls[u] = (uint8_t)ucls[i];
+    }
+    __syncthreads();
+
+    const int rpw = (U + kBigWarps - 1) / kBigWarps;  // rows per warp (contiguous: write locality)
+    const int r0 = warp * rpw, r1 = min(U, r0 + rpw);
+    float* obase = a.obs + (size_t)env * U * F;
+    if (done && !fresh) {  // inactive UEs observe zeros
+      for (size_t e = (size_t)r0 * F + lane; e < (size_t)r1 * F; e += 32) obase[e] = 0.0f;
+      return;
+    }
+    const int b0 = lane, b1 = lane + 32;
+    const bool h0 = b0 < B, h1 = b1 < B;    // the column exists
+    const bool v0 = b0 < nb, v1 = b1 < nb;  // the BS slot is live
+    const float2 q0 = h0 ? s.bsf[b0] : make_float2(0.0f, 0.0f), q1 = h1 ? s.bsf[b1] : make_float2(0.0f, 0.0f);
+    const int cb0 = h0 ? (int)s.cls[b0] * nuc : 0, cb1 = h1 ? (int)s.cls[b1] * nuc : 0;
+    const float kk = a.cls[0].k_hi, l0c = a.cls[0].l0_hi;
+    float bsu0 = -1.0f, bsu1 = -1.0f;
+    int cn0 = 0, cn1 = 0;
+    if (MA) {
+      if (h0) { bsu0 = s.bsu[b0]; cn0 = s.cnt[b0]; }
+      if (h1) { bsu1 = s.bsu[b1]; cn1 = s.cnt[b1]; }
+    }
+#pragma unroll 2
+    for (int u = r0; u < r1; ++u) {
+      const float2 p = s.pxy[u];
+      const uint2 cw = s.cw[u];
+      float* row = obase + (size_t)u * F;
+      // log2 snr of this lane's two BSs (d = 0 is the reference's EPSILON, channels.py:8: the 1e-32
+      // vanishes in the rounding of every d2 >= 1)
+      float dx = p.x - q0.x, dy = p.y - q0.y;
+      const float d2f0 = fmaf(dx, dx, fmaf(dy, dy, 1e-32f));
+      dx = p.x - q1.x, dy = p.y - q1.y;
+      const float d2f1 = fmaf(dx, dx, fmaf(dy, dy, 1e-32f));
+      float l0v, l1v, m0, m1;  // log2 snr, connectable range
+      if (one_class) {
+        l0v = fmaf(-kk, lg2_sfu(d2f0), l0c);
+        l1v = fmaf(-kk, lg2_sfu(d2f1), l0c);
+        m0 = m1 = d2max0f;
+      } else {
+        const int uc = (int)s.ucls[u];
+        const ClassDev& k0 = a.cls[cb0 + uc];
+        const ClassDev& k1 = a.cls[cb1 + uc];
+        l0v = k0.ltab ? k0.ltab[min((int)d2f0, k0.ltab_len - 1)] : fmaf(-k0.k_hi, lg2_sfu(d2f0), k0.l0_hi);
+        l1v = k1.ltab ? k1.ltab[min((int)d2f1, k1.ltab_len - 1)] : fmaf(-k1.k_hi, lg2_sfu(d2f1), k1.l0_hi);
+        m0 = (float)k0.d2max;
+        m1 = (float)k1.d2max;
+      }
+      if (!v0) l0v = -INFINITY;
+      if (!v1) l1v = -INFINITY;
+      const float lmax = warp_max_f32(fmaxf(l0v, l1v));
+      if (h0) {
+        row[b0] = ((cw.x >> lane) & 1u) ? 1.0f : 0.0f;
+        row[B + b0] = ex2_sfu(l0v - lmax);  // snr / max snr (a dead slot: ex2(-inf) = 0)
+      }
+      if (h1) {
+        row[b1] = ((cw.y >> lane) & 1u) ? 1.0f : 0.0f;
+        row[B + b1] = ex2_sfu(l1v - lmax);
+      }
+      if (lane == 0) row[2 * B] = s.ut[u];
+      if (MA) {
+        const bool ok0 = v0 && d2f0 <= m0, ok1 = v1 && d2f1 <= m1;  // available_connections (base.py:216-218)
+        const int tot = __reduce_add_sync(kFull, (ok0 ? cn0 : 0) + (ok1 ? cn1 : 0));
+        const float inv = 1.0f / fmaxf(1.0f, (float)tot);
+        if (h0) {
+          row[2 * B + 1 + b0] = ok0 ? bsu0 : -1.0f;
+          row[3 * B + 1 + b0] = ok0 ? (float)cn0 * inv : 0.0f;
+        }
+        if (h1) {
+          row[2 * B + 1 + b1] = ok1 ? bsu1 : -1.0f;
+          row[3 * B + 1 + b1] = ok1 ? (float)cn1 * inv : 0.0f;
+        }
+      }
+    }
+  };
+
+  // ================= run =================
+  if (op == OP_RESET) {
+    reinit_all();
+#pragma unroll
+    for (int i = 0; i < kBigMaxI; ++i) {
+      const int u = tid + i * kBigThreads;
+      if (u >= U) continue;
+      const size_t idx = (size_t)env * U + u;
+      util[i] = -1.0f;
+      a.utility[idx] = -1.0f;
+      if (a.rate) a.rate[idx] = 0.0;
+      if (!GYM) a.assoc[idx] = -1;
+      if (GYM && MA) a.reward[idx] = 0.0f;
+    }
+    util_known = true;
+    if (tid == 0) {
+      a.done[env] = 0;
+      if (GYM && !MA) a.reward[env] = 0.0f;
+    }
+    phase_post();
+  } else if (op == OP_OBSERVE) {
+    phase_post();
+  } else if (!GYM) {
+    if (ph & 1) phase_move();  // FORK moves first (base.py:232-233)
+    if (ph & 2) phase_pre();
+    if (ph & 4) phase_clock();
+  } else {
+    if (ph & 2) phase_pre();
+    if (ph & 1) phase_move();
+    if (ph & 4) phase_clock();
+    if (ph & 8) phase_post();
   }
 
   // ---- store state ----
-  if (touched) {
+  if (op != OP_OBSERVE) {
 #pragma unroll
     for (int i = 0; i < kBigMaxI; ++i) {
       const int u = tid + i * kBigThreads;
@@ -457,7 +558,7 @@ __global__ void __launch_bounds__(kBigThreads) step_big_kernel(const __grid_cons
       }
     }
     if (tid == 0) {
-      a.t[env] = t_e;
+      if ((ph & 4) || op == OP_RESET) a.t[env] = t_e;
       if (fresh) a.episode[env] = epi;
     }
   }

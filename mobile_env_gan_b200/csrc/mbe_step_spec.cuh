@@ -59,7 +59,7 @@ struct ChunkMem {
 // One fused step of the EPB envs starting at env_base.  PIPE: the state comes from shared memory
 // (ChunkMem::st_*), otherwise straight from global memory.  The observation block is left in
 // m.obs; the caller stores it.
-template <int MODE, int HANDLER, int U, int B, bool PER_ENV, bool PIPE>
+template <int MODE, int HANDLER, int U, int B, bool PER_ENV, bool PIPE, bool MC = false>
 __device__ __forceinline__ void step_chunk(const StepArgs& a, const int env_base, const ChunkMem& m) {
   constexpr bool GYM = (MODE == 1);
   constexpr bool MA = (HANDLER == 1);
@@ -89,9 +89,10 @@ __device__ __forceinline__ void step_chunk(const StepArgs& a, const int env_base
   const unsigned idx = (unsigned)env_ld * U + (valid ? u : 0);
   const unsigned gid = a.env_offset + (unsigned)env;
   uint32_t* bs_env = PER_ENV ? s_bs + (size_t)min(env_in_blk, EPB - 1) * B : nullptr;
-  // the slot's class constants (BSs of a shared layout may differ in bw/freq/tx/height,
-  // entities.py:6-29; per-env random layouts have one class): constant-bank operands once unrolled
-  auto SL = [&](int b) -> const SlotDev& { return a.slot[PER_ENV ? 0 : b]; };
+  // the slot's class constants.  MC: the BSs of a shared layout differ in bw/freq/tx/height
+  // (entities.py:6-29) -- every slot has its own folded class, constant-bank operands once the loops
+  // over b unroll; otherwise all slots share slot 0's (one register set)
+  auto SL = [&](int b) -> const SlotDev& { return a.slot[MC ? b : 0]; };
 
   // ---- load state (all loads issued before any use) ----
   const unsigned lidx = valid ? (unsigned)(env_in_blk * U + u) : 0u;  // index inside the chunk
@@ -344,7 +345,7 @@ __device__ __forceinline__ void step_chunk(const StepArgs& a, const int env_base
 }
 
 // ---- one chunk per CTA (works for any E; also the fallback of the pipelined kernel) ----
-template <int MODE, int HANDLER, int U, int B, bool PER_ENV>
+template <int MODE, int HANDLER, int U, int B, bool PER_ENV, bool MC = false>
 __global__ void __launch_bounds__(kThreads, MBE_SPEC_MIN_BLOCKS(MODE, HANDLER, B)) step_spec_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool GYM = (MODE == 1);
@@ -371,8 +372,15 @@ __global__ void __launch_bounds__(kThreads, MBE_SPEC_MIN_BLOCKS(MODE, HANDLER, B
     for (int i = threadIdx.x; i < n; i += kThreads) m.bs[i] = g[i];
     __syncthreads();
   }
-  step_chunk<MODE, HANDLER, U, B, PER_ENV, false>(a, env_base, m);
+  step_chunk<MODE, HANDLER, U, B, PER_ENV, false, MC>(a, env_base, m);
   if (GYM) store_obs_block(a, m.obs, env_base, threadIdx.x, true);
+}
+
+// the multi-class instantiation of a shape (shared layouts only)
+template <int MODE, int HANDLER, int U, int B, bool PER_ENV>
+constexpr auto spec_mc_kernel() -> void (*)(StepArgs) {
+  if constexpr (PER_ENV) return nullptr;
+  else return step_spec_kernel<MODE, HANDLER, U, B, false, true>;
 }
 
 // ---- persistent, software-pipelined variant (E must be a multiple of EPB) ----

@@ -465,7 +465,7 @@ def test_readme_pathloss_example_runs_verbatim_and_matches_the_oracle():
     config['channel_params'].update({'gamma': 2.0})
 
     # create environment with custom channel model
-    config.update({"num_envs": 4, "ue": dict(config["ue"], snr_tr=2e-3, velocity=9.0)})  # a range that bites on 200 x 200
+    config.update({"num_envs": 4, "ue": dict(config["ue"], snr_tr=3.0, velocity=9.0)})  # snr > 3: about 58 map units
     env = gymnasium.make('mobile-small-central-v0', config=config)
     # ...
     assert env.mode == "gym" and env.plan.classes[0]["log2snr_lut"] is None  # affine in log-distance: SFU path
@@ -478,7 +478,7 @@ def test_readme_pathloss_example_runs_verbatim_and_matches_the_oracle():
     env.reset()
     env.inject_waypoints(wp)
     env.set_positions(init)
-    p = orc.Params(velocity=9.0, snr_tr=2e-3, channel=("pathloss", 2.0))
+    p = orc.Params(velocity=9.0, snr_tr=3.0, channel=("pathloss", 2.0))
     bs_xy = env.bs_xy.cpu().tolist()
     refs = []
     for e in range(E):
@@ -502,3 +502,51 @@ def test_readme_pathloss_example_runs_verbatim_and_matches_the_oracle():
             close(got[fin], o[fin], "observation")
             ranged += sum(1 for u in range(U) for b in range(B) if not refs[e].connectable(b, u))
     assert ranged > 0  # the threshold really cut links
+
+
+@pytest.mark.parametrize("wire", ["compact", "raw"])
+@pytest.mark.parametrize("handler", ["central", "ma"])
+def test_step_host_wire_formats_reproduce_the_device_observation(wire, handler, monkeypatch):
+    """mbe_step_host ships observations in the compact wire format (mask bits + snr ratios + utility,
+    per-env BS utilities for the multi-agent handler) and expands them with host threads -- or, with
+    MBE_HOST_WIRE=raw, as plain FP32 rows by DMA.  Either way obs_host must equal the device tensor bit
+    for bit, including the all-zero rows of finished episodes (no autoreset) and fresh rows after a reset."""
+    import mobile_env_gan_b200 as mbe
+
+    monkeypatch.setenv("MBE_HOST_WIRE", wire)
+    monkeypatch.setenv("MBE_HOST_THREADS", "5")
+    E = 6400
+    env = mbe.make(f"mobile-medium-{handler}-v0", num_envs=E, autoreset=False)
+    env.reset()
+    U, B = env.NUM_USERS, env.NUM_STATIONS
+    obs_h = torch.empty(tuple(env.obs.shape), dtype=torch.float32).pin_memory()
+    rew_h = torch.empty(tuple(env.reward.shape), dtype=torch.float32).pin_memory()
+    done_h = torch.empty(E, dtype=torch.uint8).pin_memory()
+    gen = torch.Generator().manual_seed(2)
+    for k in range(env.EP_MAX_TIME + 1):
+        if k == env.EP_MAX_TIME:  # every env is done: reset a third of them, the rest stay inactive
+            mask = (torch.arange(E) % 3 == 0)
+            env.reset(env_mask=mask.cuda())
+        acts = torch.randint(0, B + 1, (E, U), dtype=torch.int32, generator=gen).pin_memory()
+        obs_h.fill_(7.0)
+        env.step_host(acts, obs_h, rew_h, done_h)
+        assert torch.equal(obs_h, env.obs.cpu()), (wire, handler, k)
+        assert torch.equal(rew_h, env.reward.cpu()) and torch.equal(done_h, env.done.cpu())
+    assert bool((env.obs.view(E, -1).abs().sum(dim=1) == 0).any())  # inactive envs were part of the comparison
+
+
+def test_step_host_compact_wire_on_a_wide_shape():
+    """Two mask words per UE (40 BSs), multi-agent, block-per-env kernel, env windows."""
+    from test_gpu_parity import wide_env
+
+    env, B, U = wide_env("wide_pf", "gym", "ma", 800, autoreset=True)
+    env.reset()
+    obs_h = torch.empty(tuple(env.obs.shape), dtype=torch.float32).pin_memory()
+    rew_h = torch.empty(tuple(env.reward.shape), dtype=torch.float32).pin_memory()
+    done_h = torch.empty(800, dtype=torch.uint8).pin_memory()
+    gen = torch.Generator().manual_seed(3)
+    for k in range(9):
+        acts = torch.randint(0, B + 1, (800, U), dtype=torch.int32, generator=gen).pin_memory()
+        env.step_host(acts, obs_h, rew_h, done_h)
+        assert torch.equal(obs_h, env.obs.cpu()), k
+        assert torch.equal(rew_h, env.reward.cpu()) and torch.equal(done_h, env.done.cpu())

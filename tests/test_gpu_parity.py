@@ -947,10 +947,137 @@ def test_errors_are_loud():
 
     with pytest.raises(MbeError):
         make_env(SCENARIOS["small"][0], 2000, {"num_envs": 4})  # U > 1024 has no kernel
+    with pytest.raises(MbeError):  # the block-per-env kernel measures distances in exact FP32: d2 < 2^24
+        wide_env("wide_rf", "gym", "central", 4, autoreset=False,
+                 extra={"width": 5000, "height": 5000, "movement_params": {"width": 5000, "height": 5000}})
     wide, _, _ = wide_env("wide_rf", "gym", "central", 4, autoreset=False)
-    wide.reset()
     with pytest.raises(MbeError):
-        wide.stage(1)  # split phases only exist on the warp-segment kernels
+        wide.step_window(1, 2)  # windows start at a multiple of 32 envs
     env = make_env(SCENARIOS["small"][0], 5, {"num_envs": 4})
     with pytest.raises(RuntimeError):
         env.step(0, 0)  # reset() first
+
+
+# ------------------------------------------- block-per-env kernel: every entry point of the ABI
+@pytest.mark.parametrize("name,mode,handler", [("wide_pf", "gym", "ma"), ("wide_rf", "gym", "central"),
+                                               ("synthetic", "gym", "ma"), ("wide_rf", "fork", "central")])
+def test_wide_split_phases_observe_and_windows_equal_the_fused_step(name, mode, handler):
+    """mbe_stage (one launch per phase), mbe_observe and mbe_step_window on the block-per-env kernel
+    reproduce its fused step bit for bit, over an episode end with autoreset."""
+    from mobile_env_gan_b200 import _lib
+
+    E = 34 if name == "synthetic" else 40
+    fused, B, U = wide_env(name, mode, handler, E, autoreset=True)
+    split, _, _ = wide_env(name, mode, handler, E, autoreset=True)
+    wins, _, _ = wide_env(name, mode, handler, E, autoreset=True)
+    for env in (fused, split, wins):
+        env.reset()
+    gym = mode == "gym"
+    names = ["pos", "wp", "t", "episode", "rate", "utility_scaled", "metrics", "done"] + (
+        ["conn", "obs", "reward"] if gym else ["assoc"])
+    order = ([_lib.PHASE_PRE, _lib.PHASE_MOVE, _lib.PHASE_CLOCK, _lib.PHASE_POST] if gym else
+             [_lib.PHASE_MOVE, _lib.PHASE_PRE, _lib.PHASE_CLOCK])
+    rng = np.random.default_rng(5)
+    side = torch.cuda.Stream()
+    for k in range(10):
+        if gym:
+            acts = torch.from_numpy(rng.integers(0, B + 1, size=(E, U)).astype(np.int32)).cuda()
+            fused.step(acts)
+            split.actions.copy_(acts)
+            wins.actions.copy_(acts)
+        else:
+            fused.step(0, k)
+        for phase in order:
+            split.stage(phase)
+        torch.cuda.synchronize()
+        wins.step_window(32, E - 32, stream=side)
+        wins.step_window(0, 32)
+        torch.cuda.synchronize()
+        for n in names:
+            assert torch.equal(getattr(split, n), getattr(fused, n)), (n, k)
+            assert torch.equal(getattr(wins, n), getattr(fused, n)), (n, k)
+        if gym:
+            before = fused.obs.clone()
+            fused.obs.zero_()
+            fused.observe()
+            assert torch.equal(fused.obs, before), k
+
+
+def test_wide_debug_snr_matches_oracle():
+    env, B, U = wide_env("wide_rf", "gym", "central", 8, autoreset=False)
+    mir = Mirror(env)
+    env.reset(), mir.reset()
+    snr = env.enable_debug_snr()
+    from oracle import mbe_oracle as orc
+
+    for k in range(3):
+        acts = np.zeros((8, U), dtype=np.int32)
+        want, _ = orc.batch_snr(mir.p, mir.pos, mir.bs)
+        env.step(torch.from_numpy(acts).cuda())
+        mir.step_gym(acts)
+        got = snr.cpu().numpy().astype(np.float64)
+        fin = want < 3e38
+        close(got[fin], want[fin], f"snr step {k}")
+
+
+def test_full_size_synthetic_matches_compiled_oracle():
+    """BASELINE configs[4] at FULL size: 64 BS x 512 UE, ProportionalFair, 16,384 envs (8.4 M UEs, 537 M
+    links per step) against the compiled restatement, two steps -- connection sets, positions, done exact,
+    rates up to rounding flips, utilities / reward / observations 1e-5 (compared in env slices)."""
+    CEnvBatch = _compiled_oracle()
+    E = 16384
+    env, B, U = wide_env("synthetic", "gym", "central", E, autoreset=False)
+    mir = Mirror(env)
+    env.reset()
+    mir._reinit(np.ones(E, dtype=bool))
+    c = CEnvBatch(mir.p, mir.bs, E, U, handler="central")
+    c.reset(mir.pos)
+    rng = np.random.default_rng(4)
+    for k in range(2):
+        acts = rng.integers(0, B + 1, size=(E, U)).astype(np.int32)
+        mir.t = c.t.astype(np.int64)
+        c.step_gym(acts, mir.new_wp())
+        obs, rew, _, trunc, _ = env.step(torch.from_numpy(acts).to(env.device))
+        assert np.array_equal(env.pos.cpu().numpy(), c.pos), k
+        assert np.array_equal(trunc.cpu().numpy(), c.done.astype(bool)), k
+        close(rew.cpu(), c.reward, f"reward {k}")
+        flips = 0
+        for lo in range(0, E, 1024):
+            sl = slice(lo, lo + 1024)
+            assert np.array_equal(conn_bool_from_words(env.conn[sl].cpu().numpy(), B), c.conn[sl].astype(bool)), (k, lo)
+            diff = np.abs(env.rate[sl].cpu().numpy() - c.rate[sl])
+            assert float(diff.max(initial=0.0)) <= 0.0100001
+            flips += int((diff > 0).sum())
+            close(env.utility_scaled[sl].cpu(), c.util[sl], f"utility {k}")
+            close(obs[sl].cpu().numpy().reshape(1024, U, -1), c.obs[sl], f"obs {k}")
+        assert flips <= 64, flips  # of 8.4 M rates
+
+
+def test_full_size_large_central_matches_compiled_oracle():
+    """BASELINE configs[3] at FULL size: mobile-large-central-v0 (13 BS x 30 UE) on 262,144 envs, five
+    Philox-driven steps against the compiled restatement."""
+    import mobile_env_gan_b200 as mbe
+
+    CEnvBatch = _compiled_oracle()
+    E = 262144
+    env = mbe.make("mobile-large-central-v0", num_envs=E)
+    mir = Mirror(env)
+    env.reset()
+    mir._reinit(np.ones(E, dtype=bool))
+    U, B = mir.U, mir.B
+    c = CEnvBatch(mir.p, mir.bs, E, U, handler="central")
+    c.reset(mir.pos)
+    rng = np.random.default_rng(9)
+    for k in range(5):
+        acts = rng.integers(0, B + 1, size=(E, U)).astype(np.int32)
+        mir.t = c.t.astype(np.int64)
+        c.step_gym(acts, mir.new_wp())
+        obs, rew, _, trunc, _ = env.step(torch.from_numpy(acts).to(env.device))
+        assert np.array_equal(conn_bool_from_words(env.conn.cpu().numpy(), B), c.conn.astype(bool)), k
+        assert np.array_equal(env.pos.cpu().numpy(), c.pos), k
+        assert np.array_equal(trunc.cpu().numpy(), c.done.astype(bool)), k
+        _few_rounding_flips(env.rate.cpu().numpy(), c.rate, f"rate step {k}", max_flips=16)
+        close(env.utility_scaled.cpu(), c.util, f"utility {k}")
+        close(rew.cpu(), c.reward, f"reward {k}")
+        for lo in range(0, E, 32768):
+            close(obs[lo:lo + 32768].cpu().numpy().reshape(32768, U, -1), c.obs[lo:lo + 32768], f"obs {k}")
