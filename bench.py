@@ -13,9 +13,10 @@ footprint exceeds the 126 MB L2 (``config.l2``).  Steps are replayed from a CUDA
 Printed JSON line (rank 0): value = whole-job env-steps/s with inputs resident in HBM;
 e2e = the same metric through the host-buffer C-ABI call (mbe_step_host: pinned host actions
 in, obs/reward/done out, copies inside the timed region); roofline = algorithmic bytes of the
-step kernel / its average duration against the measured HBM peak; cpu_baseline = the oracle's
-scalar-Python port of the reference step timed on this box's host cores (the reference's own speed
-class), with ``cpu_baseline.compiled`` = the same arithmetic as a compiled C + OpenMP restatement.
+step kernel / its average duration against the measured HBM peak; cpu_baseline = the UNMODIFIED
+reference's MComCore.step (oracle/_ref, kind "reference"; the oracle's scalar-Python port where the
+reference is not installed) timed on this box's host cores, with ``cpu_baseline.port`` = the scalar
+port and ``cpu_baseline.compiled`` = the same arithmetic as a compiled C + OpenMP restatement.
 Secondary keys (never used for value / roofline): e2e.obs_stays_on_device, two_env_groups_in_flight,
 fused_episode (FORK workloads, mbe_rollout).
 """
@@ -156,8 +157,12 @@ def make_config(args):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle scalar port; the Python reference
-    itself cannot travel to the GPU box) on all host cores; each step is a bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores; each step
+    is a bounded sample.  Where the reference is installed (oracle/_ref, built by build() from
+    /root/reference with pip --no-deps; it travels to the GPU box) every process steps the UNMODIFIED
+    ``MComCore.step`` (kind "reference": the fork's FORK-order step -- it has no actions or observations --
+    on the workload's layout, JSON dumps off); otherwise the oracle's scalar port
+    of the same step (kind "port")."""
     if rank != 0:
         return
     from oracle import cpu_baseline
@@ -167,7 +172,8 @@ def run_reference(args, rank, world):
     total_steps = args.warmup + args.steps
     # every step is a bounded sample; the whole run is held to about two minutes whatever K is
     seconds = max(0.02, min(5.0, 120.0 / max(total_steps, 1)))
-    runner = cpu_baseline.Runner(workload, procs)
+    kind = "reference" if cpu_baseline.reference_installed() else "port"
+    runner = cpu_baseline.Runner(workload, procs, kind=kind)
     vals = []
     for i in range(total_steps):
         r = runner.step(seconds)
@@ -183,7 +189,7 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": make_config(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind,
                          "sample": vals[-1]["sample"] + "; each step = every host core stepping its own env for a "
                                    "bounded time", "single_core": vals[-1]["single_core"], "compiled": compiled},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -220,8 +226,15 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_baseline
 
-        cpu = cpu_baseline.run(args.workload, args.cpu_seconds, os.cpu_count() or 1)
-        # beside the faithful (scalar Python, like the reference) port: the same arithmetic compiled
+        procs = os.cpu_count() or 1
+        port = cpu_baseline.run(args.workload, args.cpu_seconds, procs)
+        # the unmodified reference where it is installed (oracle/_ref), else the oracle's scalar port
+        cpu = cpu_baseline.run_reference(args.workload, args.cpu_seconds, procs) or port
+        if cpu is not port:
+            cpu["port"] = port  # the scalar restatement (GYM order with observations for the GYM workloads)
+            if args.workload == "mobile-custom-v0":  # the fork as shipped: four JSON dumps per step
+                cpu["as_shipped"] = cpu_baseline.run_reference(args.workload, min(2.0, args.cpu_seconds), procs, dumps=True)
+        # beside them: the same arithmetic as a compiled C + OpenMP restatement
         cpu["compiled"] = cpu_baseline.run_compiled(args.workload, min(2.0, args.cpu_seconds))
 
     # pin this rank to the CPUs / NUMA node next to its GPU before any pinned host buffer exists,

@@ -104,7 +104,7 @@ struct mbe_env {
   unsigned char* wire_dev = nullptr;     // [E * bytes_per_env]
   unsigned char* wire_pinned = nullptr;  // the same, pinned host staging
   std::vector<cudaEvent_t> wire_events;  // one per env window
-  std::unique_ptr<mbe::WorkerPool> wire_pool;
+  std::unique_ptr<mbe::ExpandCrew> wire_pool;
 };
 
 namespace {
@@ -847,8 +847,10 @@ int mbe_step_host(mbe_env* env, const int32_t* actions_host, float* obs_host, fl
     const char* tv = std::getenv("MBE_HOST_THREADS");
     cpu_set_t set;
     int cpus = (sched_getaffinity(0, sizeof set, &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
-    const int threads = tv ? std::max(1, std::atoi(tv)) : std::max(1, std::min(cpus, 32));
-    env->wire_pool.reset(new mbe::WorkerPool(threads - 1));  // the calling thread is the last worker
+    // spinning workers: keep clear of oversubscription (driver threads, other ranks); 8 threads expand a
+    // 65,536-env medium batch in 0.3 ms on the B200 box's host (profiles/host_expand_bench.cu)
+    const int threads = tv ? std::max(1, std::atoi(tv)) : std::max(1, std::min(cpus / 2, 8));
+    env->wire_pool.reset(new mbe::ExpandCrew(threads - 1));  // the calling thread is the last worker
   }
   if (compact)
     while ((int)env->wire_events.size() < windows) {
@@ -860,6 +862,29 @@ int mbe_step_host(mbe_env* env, const int32_t* actions_host, float* obs_host, fl
     MBE_CUDA(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
     MBE_CUDA(cudaEventCreateWithFlags(&env->host_fork, cudaEventDisableTiming));
     MBE_CUDA(cudaEventCreateWithFlags(&env->host_join, cudaEventDisableTiming));
+  }
+  // the expansion crew is woken first: its wake-up overlaps the launches below.  Any early return
+  // (a failing CUDA call) releases it through the guard.
+  struct CrewGuard {
+    mbe::ExpandCrew* crew;
+    ~CrewGuard() {
+      if (crew) crew->abort();
+    }
+  } crew_guard{nullptr};
+  if (compact) {
+    mbe::ExpandCrew* crew = env->wire_pool.get();
+    if (windows > mbe::ExpandCrew::kMaxWindows) return fail("mbe_step_host: at most %d env windows", mbe::ExpandCrew::kMaxWindows);
+    const mbe::WireShape ws = env->wire_shape;
+    const int chunks = std::max(1, 4 * (crew->size() + 1));
+    const unsigned char* pinned = env->wire_pinned;
+    const int E = a.E, UF = a.U * a.F;
+    crew->begin(windows, chunks, [=](int w, int c) {
+      const int first = w * per, count = std::min(per, E - first);
+      const int lo = (int)((long long)count * c / chunks), hi = (int)((long long)count * (c + 1) / chunks);
+      if (hi > lo)
+        mbe::wire_expand_any(pinned + (size_t)first * ws.bytes_per_env(), obs_host + (size_t)first * UF, count, lo, hi, ws);
+    });
+    crew_guard.crew = crew;
   }
   if (windows > 1) {  // the side stream starts after everything already queued on the caller's stream
     MBE_CUDA(cudaEventRecord(env->host_fork, st));
@@ -883,6 +908,7 @@ int mbe_step_host(mbe_env* env, const int32_t* actions_host, float* obs_host, fl
       mbe::wire_pack_kernel<<<(rows + 255) / 256, 256, 0, s>>>(env->bufs.obs, env->wire_dev + off, first, count, ws);
       MBE_CUDA(cudaGetLastError());
       MBE_CUDA(cudaMemcpyAsync(env->wire_pinned + off, env->wire_dev + off, len, cudaMemcpyDeviceToHost, s));
+      MBE_CUDA(cudaEventRecord(env->wire_events[w], s));  // the window's observation bytes have landed
     } else if (obs_host) {
       MBE_CUDA(cudaMemcpyAsync(obs_host + fu * a.F, env->bufs.obs + fu * a.F, cu * a.F * 4, cudaMemcpyDeviceToHost, s));
     }
@@ -892,28 +918,20 @@ int mbe_step_host(mbe_env* env, const int32_t* actions_host, float* obs_host, fl
     }
     if (done_host)
       MBE_CUDA(cudaMemcpyAsync(done_host + first, env->bufs.done + first, (size_t)count, cudaMemcpyDeviceToHost, s));
-    if (compact) MBE_CUDA(cudaEventRecord(env->wire_events[w], s));
   }
   if (windows > 1) {
     MBE_CUDA(cudaEventRecord(env->host_join, env->host_stream));
     MBE_CUDA(cudaStreamWaitEvent(st, env->host_join, 0));
   }
   if (compact) {
-    // expand window after window as it lands; the pool works on window c while window c+1 is in flight
-    mbe::WorkerPool* pool = env->wire_pool.get();
-    const mbe::WireShape ws = env->wire_shape;
-    const int chunks = std::max(1, 4 * (pool->size() + 1));
-    for (int w = 0, first = 0; first < a.E; ++w, first += per) {
-      const int count = std::min(per, a.E - first);
+    // publish window after window as it lands; the crew expands window c while window c+1 is in flight
+    mbe::ExpandCrew* crew = env->wire_pool.get();
+    for (int w = 0; w < windows; ++w) {
       MBE_CUDA(cudaEventSynchronize(env->wire_events[w]));
-      const unsigned char* src = env->wire_pinned + (size_t)first * ws.bytes_per_env();
-      float* dst = obs_host + (size_t)first * a.U * a.F;
-      pool->submit(chunks, [=](int c) {
-        const int lo = (int)((long long)count * c / chunks), hi = (int)((long long)count * (c + 1) / chunks);
-        if (hi > lo) mbe::wire_expand_any(src, dst, count, lo, hi, ws);
-      });
+      crew->publish(w + 1);
     }
-    pool->wait();
+    crew->finish();
+    crew_guard.crew = nullptr;
   }
   MBE_CUDA(cudaStreamSynchronize(st));
   return 0;

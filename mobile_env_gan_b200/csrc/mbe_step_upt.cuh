@@ -38,6 +38,12 @@
 #ifndef MBE_UPT_STORE
 #define MBE_UPT_STORE 0
 #endif
+// 1 = the rate-table gathers are issued, then the movement phase runs (it needs nothing from them),
+// then the gathered values are summed: the L2 latency of the gathers hides behind ~250 instructions of
+// independent work instead of stalling the warp at the first add
+#ifndef MBE_UPT_EARLY_MOVE
+#define MBE_UPT_EARLY_MOVE 1
+#endif
 #ifndef MBE_UPT_LUT_HINT
 #define MBE_UPT_LUT_HINT 2  // read-only path for the rate table: measured -2.3% (multi-agent), neutral (central)
 #endif
@@ -180,17 +186,38 @@ __global__ void __launch_bounds__(32 * MBE_UPT_WARPS, MBE_UPT_MIN_BLOCKS(HANDLER
   float util[UPT];
   float lu = 0.0f, lr = 0.0f;
   int ln = 0;
+#if MBE_UPT_EARLY_MOVE
+  double gv[UPT][B];
+#pragma unroll
+  for (int j = 0; j < UPT; ++j)
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      const unsigned off = (unsigned)cnt[b] * stride + (unsigned)d2pre[j][b];
+      if (MA) gv[j][b] = ((conn[j] >> b) & 1u) ? upt_lut(lut + off) : 0.0;
+      else gv[j][b] = upt_lut(lut + (((conn[j] >> b) & 1u) ? off : stride - 1u));
+    }
+  // ---- move (movement.py:42-62): independent of the rates, runs while the gathers are in flight ----
+#pragma unroll
+  for (int j = 0; j < UPT; ++j) {
+    if (wx[j] < 0) next_waypoint(a, gid, (unsigned)(k + K * j), idx[j], t_e, epi, valid, wx[j], wy[j]);
+    if (move_ue(a.mv[0], x[j], y[j], wx[j], wy[j])) wx[j] = wy[j] = -1;
+  }
+#endif
 #pragma unroll
   for (int j = 0; j < UPT; ++j) {
     double r = 0.0;
 #pragma unroll
     for (int b = 0; b < B; ++b) {
+#if MBE_UPT_EARLY_MOVE
+      r += gv[j][b];  // (+0.0 for an unconnected BS: the sum's bits do not change)
+#else
       if (MA) {  // measured: predicated gathers win with the multi-agent register budget ...
         if ((conn[j] >> b) & 1u) r += upt_lut(lut + ((unsigned)cnt[b] * stride + (unsigned)d2pre[j][b]));
       } else {   // ... unconditional ones (unconnected -> the table's 0.0 entry) for the central handler
         const unsigned off = (unsigned)cnt[b] * stride + (unsigned)d2pre[j][b];
         r += upt_lut(lut + (((conn[j] >> b) & 1u) ? off : stride - 1u));
       }
+#endif
     }
     rate[j] = r;
     util[j] = scaled_utility(a, r);
@@ -246,12 +273,14 @@ __global__ void __launch_bounds__(32 * MBE_UPT_WARPS, MBE_UPT_MIN_BLOCKS(HANDLER
     }
   }
 
+#if !MBE_UPT_EARLY_MOVE
   // ---- move (movement.py:42-62) ----
 #pragma unroll
   for (int j = 0; j < UPT; ++j) {
     if (wx[j] < 0) next_waypoint(a, gid, (unsigned)(k + K * j), idx[j], t_e, epi, valid, wx[j], wy[j]);
     if (move_ue(a.mv[0], x[j], y[j], wx[j], wy[j])) wx[j] = wy[j] = -1;
   }
+#endif
 
   // ---- clock, departures, same-step autoreset (base.py:280-291, 407-409; 172-209) ----
   t_e += 1;

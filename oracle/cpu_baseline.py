@@ -65,17 +65,74 @@ def _worker(args):
     return steps, time.perf_counter() - t0
 
 
-def _summary(workload, procs, seconds, res):
+def reference_installed() -> bool:
+    """True where the unmodified reference can be executed: /root/reference (build container) or its
+    pip install under oracle/_ref (oracle/build_ref.py; travels to the GPU box)."""
+    from oracle import ref_harness
+
+    return ref_harness.reference_available()
+
+
+def _ref_worker(args):
+    """The UNMODIFIED reference's MComCore.step (mobile_env/core/base.py:230-296) -- BASELINE.md section 3:
+    a fixed-layout subclass harness for the scenario shapes (like MComCustom's custom.py:40-62), the
+    fork's MComCustom itself for mobile-custom-v0; FORK semantics (the fork's step takes no action and
+    builds no observation), default plugins, per-step JSON dumps disabled unless ``dumps``."""
+    workload, seconds, seed, dumps = args
+    import random
+    import tempfile
+
+    from oracle import ref_harness as rh
+
+    bs, U, _mode, _handler, vel, over = WORKLOADS[workload]
+    ep_time = 20
+    random.seed(seed)
+    scratch = None
+    if bs is None:
+        _, _, custom = rh.import_reference()
+        cls = custom.MComCustom
+        if dumps:  # the dump paths are relative ("../collectData2/..."): run inside a scratch directory
+            scratch = tempfile.TemporaryDirectory(prefix="mbe_ref_dumps_")
+            os.makedirs(os.path.join(scratch.name, "cwd"))
+            os.chdir(os.path.join(scratch.name, "cwd"))
+        else:
+            cls = type("MComCustomNoDumps", (cls,), {"save_layout_and_data_rates": lambda self, e, s: None})
+        env = cls({"seed": seed, "EP_MAX_TIME": ep_time})
+    else:
+        cfg = {"seed": seed, "EP_MAX_TIME": ep_time, "width": over.get("width", 200.0), "height": over.get("height", 200.0)}
+        env = rh.make_fixed_layout_env(bs, U, config=cfg, ue_params={"velocity": vel})
+    env.reset()
+    steps = epoch = s = 0
+    t0 = time.perf_counter()
+    while True:
+        env.step(epoch, s)
+        steps += 1
+        s += 1
+        if env.time_is_up:
+            epoch, s = epoch + 1, 0
+            env.reset()
+        if (steps % 8 == 0 or U > 64) and time.perf_counter() - t0 >= seconds:
+            break
+    wall = time.perf_counter() - t0
+    if scratch is not None:
+        os.chdir("/")
+        scratch.cleanup()
+    return steps, wall
+
+
+def _summary(workload, procs, seconds, res, kind="port"):
     total = sum(s for s, _ in res)
     wall = max(t for _, t in res)
+    what = ("scalar port of MComCore.step" if kind == "port" else
+            "the unmodified reference's MComCore.step from oracle/_ref, FORK semantics (the fork has no actions / "
+            "observations), default plugins, JSON dumps off")
     return {
         "value": total / wall,
         "unit": "env-steps/s",
         "cores": procs,
-        "kind": "port",
+        "kind": kind,
         "single_core": float(np.mean([s / t for s, t in res])),
-        "sample": f"{procs} procs x {seconds:.2f} s of {workload} (scalar port of MComCore.step, "
-                  f"one env per process, {total} env-steps)",
+        "sample": f"{procs} procs x {seconds:.2f} s of {workload} ({what}, one env per process, {total} env-steps)",
     }
 
 
@@ -89,18 +146,38 @@ def run(workload: str, seconds: float = 5.0, procs: int | None = None):
     return _summary(workload, procs, seconds, res)
 
 
+def run_reference(workload: str, seconds: float = 5.0, procs: int | None = None, dumps: bool = False):
+    """Like ``run`` but every process steps the UNMODIFIED reference (kind "reference"); None where the
+    reference is not installed.  ``dumps=True`` (mobile-custom-v0 only) keeps the four JSON dumps per
+    step the fork ships with (base.py:261, 298-349), written into a scratch directory."""
+    if not reference_installed():
+        return None
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_ref_worker, [(workload, seconds, 1000 + i, dumps) for i in range(procs)])
+    out = _summary(workload, procs, seconds, res, kind="reference")
+    if dumps:
+        out["sample"] = out["sample"].replace("JSON dumps off", "as shipped: 4 JSON dumps per step into a scratch directory")
+    return out
+
+
 class Runner:
     """Persistent worker pool for the ``--impl reference`` arm: one call of ``step`` = every host
     core steps its own env for ``seconds`` (a bounded sample of the workload)."""
 
-    def __init__(self, workload: str, procs: int | None = None):
+    def __init__(self, workload: str, procs: int | None = None, kind: str = "port"):
         self.workload = workload
         self.procs = procs or os.cpu_count() or 1
         self.pool = mp.get_context("spawn").Pool(self.procs)
         self.calls = 0
+        self.kind = kind  # "reference": the unmodified reference from oracle/_ref; "port": the scalar restatement
 
     def step(self, seconds: float):
         self.calls += 1
+        if self.kind == "reference":
+            args = [(self.workload, seconds, 1000 * self.calls + i, False) for i in range(self.procs)]
+            return _summary(self.workload, self.procs, seconds, self.pool.map(_ref_worker, args), kind="reference")
         args = [(self.workload, seconds, 1000 * self.calls + i) for i in range(self.procs)]
         return _summary(self.workload, self.procs, seconds, self.pool.map(_worker, args))
 

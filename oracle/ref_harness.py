@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY -- drives the *real* reference from /root/reference.
+"""TEST INFRASTRUCTURE ONLY -- drives the *real* reference from /root/reference (or its install
+under ``oracle/_ref``, see ``oracle/build_ref.py``).
 
 Nothing under ``oracle/`` is product code: only ``tests/``, ``__graft_entry__.smoke()``
 and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.
@@ -6,8 +7,10 @@ and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import 
 This module exists so that the numpy restatement in ``oracle/mbe_oracle.py`` can be
 pinned against the reference's own ``MComCore.step`` (reference
 ``mobile_env/core/base.py:230-296``) and so that golden vectors can be generated
-(``oracle/gen_golden.py`` -> ``tests/golden/*.json``).  It only works where
-``/root/reference`` exists (the build container); it never travels to the GPU box.
+(``oracle/gen_golden.py`` -> ``tests/golden/*.json``).  ``/root/reference`` exists only in the build
+container; the pip-installed copy ``oracle/_ref`` (git-ignored, built by ``build()``) travels to the
+GPU box, where only bench.py's CPU legs use it (``oracle/cpu_baseline.py``) -- the ``-m gpu`` tests and
+``smoke()`` compare against the oracle and the committed fixtures, never against this module.
 
 The reference imports shapely / matplotlib / pygame / svgpath2mpl at module top
 (``core/base.py:8-15``, ``core/util.py:3-4,24-28``, ``core/entities.py:3``); none is
@@ -23,7 +26,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("MBE_REFERENCE_ROOT", "/root/reference")
+_INSTALLED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick_root() -> str:
+    env = os.environ.get("MBE_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/mobile_env/core"):
+        return "/root/reference"
+    return _INSTALLED
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:

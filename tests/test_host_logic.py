@@ -389,3 +389,28 @@ def test_env_view_queries_match_the_reference_methods():
         vu.x = ru.x = 5000
     view.update_connections(), ref.update_connections()
     assert all(len(view.bs2ue_connections[b]) == 0 for b in v_bss) and all(len(ref.bs2ue_connections[b]) == 0 for b in r_bss)
+
+
+def test_reference_install_runs_the_unmodified_step(tmp_path):
+    """oracle/build_ref.py installs the reference with its own setup.py into oracle/_ref (what the GPU
+    box's CPU baseline executes); its files are the reference's, byte for byte, and the bench worker
+    steps it (MComCore.step, base.py:230-296) on a scenario layout and as MComCustom with dumps on."""
+    import filecmp
+
+    from oracle import build_ref, cpu_baseline
+
+    if not os.path.isdir(os.path.join(build_ref.REF_SRC, "mobile_env", "core")):
+        pytest.skip("the reference sources only exist in the build container")
+    out = build_ref.build_ref()
+    assert out and build_ref.installed()
+    for name in ("base.py", "channels.py", "movement.py", "schedules.py", "utilities.py", "entities.py"):
+        assert filecmp.cmp(os.path.join(build_ref.REF_SRC, "mobile_env", "core", name),
+                           os.path.join(out, "mobile_env", "core", name), shallow=False), name
+    steps, wall = cpu_baseline._ref_worker(("mobile-medium-central-v0", 0.05, 3, False))
+    assert steps >= 8 and wall > 0
+    cwd = os.getcwd()
+    try:
+        steps, _ = cpu_baseline._ref_worker(("mobile-custom-v0", 0.05, 3, True))
+    finally:
+        os.chdir(cwd)
+    assert steps >= 8
