@@ -494,9 +494,9 @@ def main():
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.workload),
-                "traffic_note": "ncu dram bytes of ONE cold launch: reads = the algorithmic state+action bytes; most "
-                                "output bytes were still dirty in the 126 MB L2 when the profiled launch ended "
-                                "(profiles/step_kernel_traffic.json)",
+                "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch in STEADY STATE: mean of "
+                                "launches 13-20 of this rotating-batch loop, application replay, caches not flushed "
+                                "(profiles/step_kernel_traffic.json, profiles/r02_f_traffic_*.csv)",
                 "peak_source": peak_src,
                 "kernel": f"mbe::{envs[0].step_kernel_name}<{'fork' if fork else 'gym'},{handler},U={U},B={B}>",
                 "bytes_per_env_step": bpe["layout"], "bytes_per_env_step_survey_8d": bpe["survey_8d"],

@@ -17,6 +17,7 @@ Two step semantics behind one kernel set:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -116,6 +117,16 @@ class MComCore:
             # "follow_movement": True iff movement_params.reset_rng_episode -- the fork, where that flag
             # makes every epoch replay one UE trajectory (base.py:130-134) and env index = epoch number
             "shared_trajectory": False,
+            # the fork's collect loop (collectData2.ipynb cell 4) as written: step() dumps the four JSON
+            # files of base.py:298-349 and keeps the per-epoch lists for save_epoch_data().  MComCustom
+            # (the class that loop drives) defaults to None = on when there is ONE env, like the
+            # reference, and off for batches (use export.ReferenceDumpWriter / rollout there: same files
+            # without a sync per step)
+            "dumps": False,
+            "dump_root": "..",  # the reference writes to ../collectData and ../collectData2
+            # monitor.update(self) inside step() and info = monitor.info() (base.py:272): None = like the
+            # reference when there is one env, off for batches (one clone per metric and step)
+            "monitor_in_step": None,
         }
 
     @classmethod
@@ -294,6 +305,16 @@ class MComCore:
         self._allocate()
         self._bind()
         self._needs_reset = True
+        fork = self.plan.mode == _lib.MODE_FORK
+        self.dumps = bool(config["dumps"]) if config["dumps"] is not None else (fork and self.num_envs == 1)
+        if self.dumps and not fork:
+            raise NotImplementedError("config['dumps']: the dump files are the fork's FORK-mode format")
+        self.dump_root = config["dump_root"]
+        self.monitor_in_step = (bool(config["monitor_in_step"]) if config["monitor_in_step"] is not None
+                                else self.num_envs == 1)
+        # the reference's per-epoch lists (base.py:99-100, 208-209; custom.py:60-62), env 0's view
+        self.users_dataRateList = self.users_trajectoryList = self.userQoEList = None
+        self._history = None
 
     def _create_handle(self):
         p = self.plan
@@ -422,6 +443,8 @@ class MComCore:
         _lib.check(self._lib.mbe_reset(self._handle, mask_ptr, self._stream()))
         self.monitor.reset()
         self._needs_reset = False
+        if self.dumps:
+            self._begin_epoch_history()
         if self.plan.mode == _lib.MODE_GYM:
             return self._obs_view(), {}
         return None
@@ -438,13 +461,112 @@ class MComCore:
             raise RuntimeError("call reset() before step()")
         if self.plan.mode == _lib.MODE_FORK:
             _lib.check(self._lib.mbe_step(self._handle, self._stream()))
+            if self.dumps:  # base.py:261-269: the four JSON files and the per-epoch lists
+                epoch_number, curr_step = args if len(args) == 2 else (0, len(self._history["pos"]))
+                self._record_step()
+                self.save_layout_and_data_rates(epoch_number, curr_step)
+            if self.monitor_in_step:
+                self.monitor.update(self)  # base.py:272
             return None
         (actions,) = args
         if actions is not self.actions:
             self.actions.copy_(torch.as_tensor(actions).reshape(self.actions.shape), non_blocking=True)
         _lib.check(self._lib.mbe_step(self._handle, self._stream()))
+        info = {"metrics": self.metrics}
+        if self.monitor_in_step:
+            self.monitor.update(self)
+            info.update(self.monitor.info())
         # views only: no extra kernels on the step path (truncated aliases the done bytes)
-        return self._obs_view(), self.reward, self._terminated, self.done.view(torch.bool), {"metrics": self.metrics}
+        return self._obs_view(), self.reward, self._terminated, self.done.view(torch.bool), info
+
+    # ---------------------------------------------- the fork's dump methods (env level) ----
+    # Slow path by construction, like the reference: every step synchronises and copies the few
+    # tensors a dump needs.  Env i of the batch plays epoch ``epoch_number + i``.  Batched collection
+    # without the per-step sync: export.ReferenceDumpWriter (same files, byte for byte).
+    def _util_params(self):
+        up = self.config["utility_params"]
+        return up["lower"], up["upper"], tuple(up["coeffs"])
+
+    def _layouts(self):
+        if self.nbs is None:
+            bs = self.bs_xy.cpu().numpy()
+            return [bs for _ in range(self.num_envs)]
+        bs_all, nbs = self.bs_xy.cpu().numpy(), self.nbs.cpu().numpy()
+        return [bs_all[i, : nbs[i]] for i in range(self.num_envs)]
+
+    def _begin_epoch_history(self):
+        ids = sorted(self.userDict)
+        self.users_dataRateList = {u: [] for u in ids}
+        self.users_trajectoryList = {u: [] for u in ids}
+        self.userQoEList = {u: [] for u in ids}
+        self._history = {"pos": [], "arrived": [], "assoc": [], "rate": [], "bs": None}
+
+    def _record_step(self):
+        from ..export import scaled_utility_fp64
+
+        if self._history is None:
+            self._begin_epoch_history()
+        h = self._history
+        if h["bs"] is None:
+            h["bs"] = self._layouts()
+        pos, wp = self.pos.cpu().numpy(), self.wp.cpu().numpy()
+        assoc, rate = self.assoc.cpu().numpy(), self.rate.cpu().numpy()
+        h["pos"].append(pos), h["arrived"].append(wp[:, :, 0] < 0), h["assoc"].append(assoc), h["rate"].append(rate)
+        lower, upper, coeffs = self._util_params()
+        for u in self.users_dataRateList:  # env 0 under the reference's attribute names (base.py:264-269)
+            r = np.float64(rate[0][u]) if assoc[0][u] >= 0 else 0.0
+            x, y = pos[0][u]
+            self.users_dataRateList[u].append(round(r, 2))
+            self.users_trajectoryList[u].append((int(x), int(y)) if wp[0][u][0] < 0 else (np.int64(x), np.int64(y)))
+            self.userQoEList[u].append(round(scaled_utility_fp64(r, lower, upper, coeffs), 2))
+
+    def _write_files(self, files):
+        for rel, text in files.items():
+            path = os.path.join(self.dump_root, rel)
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            with open(path, "w") as f:
+                f.write(text)
+
+    def save_layout_and_data_rates(self, epoch_number, curr_step):
+        """base.py:298-349: stations_info / user_positions / data_rates / user_qoe JSON files of the
+        current step under ``<dump_root>/collectData``, one set per env (epoch ``epoch_number + i``)."""
+        from ..export import format_step_files
+
+        if self.plan.mode != _lib.MODE_FORK:
+            raise NotImplementedError("the dump files are the fork's FORK-mode format")
+        if not self._history or not self._history["pos"]:
+            self._record_step()
+        h = self._history
+        for i in range(self.num_envs):
+            self._write_files(format_step_files(epoch_number + i, curr_step, h["bs"][i], h["pos"][-1][i],
+                                                h["assoc"][-1][i], h["rate"][-1][i], self._util_params()))
+
+    def save_base_station_positions(self, epoch_number):
+        """custom.py:79-85: ``<dump_root>/collectData2/BaseStationPosition/stations_<epoch>.json``."""
+        import json
+
+        from ..export import EPOCH_DIRS
+
+        for i, bs in enumerate(self._layouts()):
+            positions = {b: (int(x), int(y)) for b, (x, y) in enumerate(bs)}
+            self._write_files({os.path.join(*EPOCH_DIRS["stations"]).format(e=epoch_number + i): json.dumps(positions)})
+
+    def save_epoch_data(self, epoch_number):
+        """base.py:351-404: the per-epoch CSV files (data rates, trajectories, QoE) from the lists the
+        dumping ``step`` kept since the last ``reset``."""
+        from ..export import EPOCH_DIRS, format_epoch_files
+
+        h = self._history
+        if not h or not h["pos"]:
+            print(f"warning: no user data rates in epoch {epoch_number}, nothing saved")  # cf. base.py:353-355
+            return
+        stations_key = os.path.join(*EPOCH_DIRS["stations"])
+        for i in range(self.num_envs):
+            files = format_epoch_files(epoch_number + i, h["bs"][i], [p[i] for p in h["pos"]],
+                                       [a[i] for a in h["arrived"]], [a[i] for a in h["assoc"]],
+                                       [r[i] for r in h["rate"]], self._util_params())
+            files.pop(stations_key.format(e=epoch_number + i), None)  # written by save_base_station_positions
+            self._write_files(files)
 
     def rollout(self, steps: int, qoe_acc=None, threshold: float = 0.0, record=()):
         """FORK mode: ``steps`` consecutive ``step`` calls (the fork's collect loop

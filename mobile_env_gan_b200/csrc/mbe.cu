@@ -825,11 +825,14 @@ int mbe_step_host(mbe_env* env, const int32_t* actions_host, float* obs_host, fl
     return fail("mbe_step_host: actions, obs and reward only exist in GYM mode");
   // Env windows on two streams: the action upload and the step of window c+1 overlap the result
   // download of window c (PCIe is full duplex).  With observations the call is bound by their
-  // download; they cross PCIe in the compact wire format (mbe_host_wire.cuh) and host threads expand
-  // window c into obs_host while window c+1 is still arriving (MBE_HOST_WIRE=raw: plain FP32 rows by
-  // DMA, no host threads).  MBE_HOST_WINDOWS / MBE_HOST_THREADS override the defaults.
+  // download: plain FP32 rows by DMA straight into obs_host (48 GB/s on the B200 box, no host thread
+  // touches them).  MBE_HOST_WIRE=compact ships them in the compact wire format instead
+  // (mbe_host_wire.cuh, a third fewer bytes) and host threads expand window c into obs_host while
+  // window c+1 is still arriving: that pays only on a host whose cores can write the FP32 rows faster
+  // than PCIe delivers them -- on the 16-vCPU B200 box it measured 0.52-0.70x the DMA path
+  // (profiles/README.md), hence opt-in.  MBE_HOST_WINDOWS / MBE_HOST_THREADS override the defaults.
   const char* wire_v = std::getenv("MBE_HOST_WIRE");
-  const bool compact = obs_host != nullptr && !(wire_v && std::strcmp(wire_v, "raw") == 0);
+  const bool compact = obs_host != nullptr && wire_v && std::strcmp(wire_v, "compact") == 0;
   const char* wv = std::getenv("MBE_HOST_WINDOWS");
   const int want = wv ? std::max(1, std::atoi(wv)) : (obs_host ? (compact ? 8 : 4) : 1);
   constexpr int kAlign = 384;  // multiple of every kernel's envs-per-CTA and of 32 (16-byte aligned slices)

@@ -15,6 +15,7 @@
 //     three passes over a padded tile, 2x the instructions; profiles/README.md.)
 // Same arithmetic helpers as the warp-segment kernels (mbe_device.cuh).
 #pragma once
+#include <type_traits>
 #include "mbe_device.cuh"
 
 #ifndef MBE_BIG_MIN_BLOCKS
@@ -264,6 +265,7 @@ __global__ void __launch_bounds__(kBigThreads, MBE_BIG_MIN_BLOCKS) step_big_kern
       for (int w = 0; w < 2; ++w) {  // one 32-bit mask word at a time (no per-BS word select)
         uint32_t ew = 0;
         const int b_lo = 32 * w, b_hi = min(nb, 32 * w + 32);
+#pragma unroll 4
         for (int b = b_lo; b < b_hi; ++b) {
           const float d2f = d2f_to(xf, yf, b);
           if (d2f <= (one_class ? d2max0f : (float)link(i, b).d2max)) {  // check_connectivity (base.py:212-214)
@@ -457,57 +459,70 @@ __global__ void __launch_bounds__(kBigThreads, MBE_BIG_MIN_BLOCKS) step_big_kern
       if (h0) { bsu0 = s.bsu[b0]; cn0 = s.cnt[b0]; }
       if (h1) { bsu1 = s.bsu[b1]; cn1 = s.cnt[b1]; }
     }
+    // FULL = both column groups exist for every lane (B == 64, the synthetic scale-up) and one link
+    // class: no column predicates, the row's stores are one base pointer plus immediates
+    auto rows = [&](auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      const int BB = FULL ? 64 : B;
 #pragma unroll 2
-    for (int u = r0; u < r1; ++u) {
-      const float2 p = s.pxy[u];
-      const uint2 cw = s.cw[u];
-      float* row = obase + (size_t)u * F;
-      // log2 snr of this lane's two BSs (d = 0 is the reference's EPSILON, channels.py:8: the 1e-32
-      // vanishes in the rounding of every d2 >= 1)
-      float dx = p.x - q0.x, dy = p.y - q0.y;
-      const float d2f0 = fmaf(dx, dx, fmaf(dy, dy, 1e-32f));
-      dx = p.x - q1.x, dy = p.y - q1.y;
-      const float d2f1 = fmaf(dx, dx, fmaf(dy, dy, 1e-32f));
-      float l0v, l1v, m0, m1;  // log2 snr, connectable range
-      if (one_class) {
-        l0v = fmaf(-kk, lg2_sfu(d2f0), l0c);
-        l1v = fmaf(-kk, lg2_sfu(d2f1), l0c);
-        m0 = m1 = d2max0f;
-      } else {
-        const int uc = (int)s.ucls[u];
-        const ClassDev& k0 = a.cls[cb0 + uc];
-        const ClassDev& k1 = a.cls[cb1 + uc];
-        l0v = k0.ltab ? k0.ltab[min((int)d2f0, k0.ltab_len - 1)] : fmaf(-k0.k_hi, lg2_sfu(d2f0), k0.l0_hi);
-        l1v = k1.ltab ? k1.ltab[min((int)d2f1, k1.ltab_len - 1)] : fmaf(-k1.k_hi, lg2_sfu(d2f1), k1.l0_hi);
-        m0 = (float)k0.d2max;
-        m1 = (float)k1.d2max;
-      }
-      if (!v0) l0v = -INFINITY;
-      if (!v1) l1v = -INFINITY;
-      const float lmax = warp_max_f32(fmaxf(l0v, l1v));
-      if (h0) {
-        row[b0] = ((cw.x >> lane) & 1u) ? 1.0f : 0.0f;
-        row[B + b0] = ex2_sfu(l0v - lmax);  // snr / max snr (a dead slot: ex2(-inf) = 0)
-      }
-      if (h1) {
-        row[b1] = ((cw.y >> lane) & 1u) ? 1.0f : 0.0f;
-        row[B + b1] = ex2_sfu(l1v - lmax);
-      }
-      if (lane == 0) row[2 * B] = s.ut[u];
-      if (MA) {
-        const bool ok0 = v0 && d2f0 <= m0, ok1 = v1 && d2f1 <= m1;  // available_connections (base.py:216-218)
-        const int tot = __reduce_add_sync(kFull, (ok0 ? cn0 : 0) + (ok1 ? cn1 : 0));
-        const float inv = 1.0f / fmaxf(1.0f, (float)tot);
-        if (h0) {
-          row[2 * B + 1 + b0] = ok0 ? bsu0 : -1.0f;
-          row[3 * B + 1 + b0] = ok0 ? (float)cn0 * inv : 0.0f;
+      for (int u = r0; u < r1; ++u) {
+        const float2 p = s.pxy[u];
+        const uint2 cw = s.cw[u];
+        float* row = obase + (size_t)u * F;
+        // log2 snr of this lane's two BSs (d = 0 is the reference's EPSILON, channels.py:8: the 1e-32
+        // vanishes in the rounding of every d2 >= 1)
+        float dx = p.x - q0.x, dy = p.y - q0.y;
+        const float d2f0 = fmaf(dx, dx, fmaf(dy, dy, 1e-32f));
+        dx = p.x - q1.x, dy = p.y - q1.y;
+        const float d2f1 = fmaf(dx, dx, fmaf(dy, dy, 1e-32f));
+        float l0v, l1v, m0, m1;  // log2 snr, connectable range
+        if (FULL || one_class) {
+          l0v = fmaf(-kk, lg2_sfu(d2f0), l0c);
+          l1v = fmaf(-kk, lg2_sfu(d2f1), l0c);
+          m0 = m1 = d2max0f;
+        } else {
+          const int uc = (int)s.ucls[u];
+          const ClassDev& k0 = a.cls[cb0 + uc];
+          const ClassDev& k1 = a.cls[cb1 + uc];
+          l0v = k0.ltab ? k0.ltab[min((int)d2f0, k0.ltab_len - 1)] : fmaf(-k0.k_hi, lg2_sfu(d2f0), k0.l0_hi);
+          l1v = k1.ltab ? k1.ltab[min((int)d2f1, k1.ltab_len - 1)] : fmaf(-k1.k_hi, lg2_sfu(d2f1), k1.l0_hi);
+          m0 = (float)k0.d2max;
+          m1 = (float)k1.d2max;
         }
-        if (h1) {
-          row[2 * B + 1 + b1] = ok1 ? bsu1 : -1.0f;
-          row[3 * B + 1 + b1] = ok1 ? (float)cn1 * inv : 0.0f;
+        if (!v0) l0v = -INFINITY;
+        if (!v1) l1v = -INFINITY;
+        const float lmax = warp_max_f32(fmaxf(l0v, l1v));
+        // the connection bit of this lane's column as 0.0f / 1.0f: (bit ? ~0 : 0) & bits(1.0f)
+        const float one0 = __uint_as_float((uint32_t)((int32_t)(cw.x << (31 - lane)) >> 31) & 0x3f800000u);
+        const float one1 = __uint_as_float((uint32_t)((int32_t)(cw.y << (31 - lane)) >> 31) & 0x3f800000u);
+        if (FULL || h0) {
+          row[b0] = one0;
+          row[BB + b0] = ex2_sfu(l0v - lmax);  // snr / max snr (a dead slot: ex2(-inf) = 0)
+        }
+        if (FULL || h1) {
+          row[b1] = one1;
+          row[BB + b1] = ex2_sfu(l1v - lmax);
+        }
+        if (MA) {
+          const bool ok0 = v0 && d2f0 <= m0, ok1 = v1 && d2f1 <= m1;  // available_connections (base.py:216-218)
+          const int tot = __reduce_add_sync(kFull, (ok0 ? cn0 : 0) + (ok1 ? cn1 : 0));
+          const float inv = 1.0f / fmaxf(1.0f, (float)tot);
+          if (FULL || h0) {
+            row[2 * BB + 1 + b0] = ok0 ? bsu0 : -1.0f;
+            row[3 * BB + 1 + b0] = ok0 ? (float)cn0 * inv : 0.0f;
+          }
+          if (FULL || h1) {
+            row[2 * BB + 1 + b1] = ok1 ? bsu1 : -1.0f;
+            row[3 * BB + 1 + b1] = ok1 ? (float)cn1 * inv : 0.0f;
+          }
         }
       }
-    }
+    };
+    if (B == 64 && one_class) rows(std::true_type{});
+    else rows(std::false_type{});
+    // the utility column (one element per row, stride F): 32 rows per store instruction instead of a
+    // predicated single-lane store in every row
+    for (int u = r0 + lane; u < r1; u += 32) obase[(size_t)u * F + 2 * B] = s.ut[u];
   };
 
   // ================= run =================

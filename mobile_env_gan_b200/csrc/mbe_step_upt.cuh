@@ -39,10 +39,12 @@
 #define MBE_UPT_STORE 0
 #endif
 // 1 = the rate-table gathers are issued, then the movement phase runs (it needs nothing from them),
-// then the gathered values are summed: the L2 latency of the gathers hides behind ~250 instructions of
-// independent work instead of stalling the warp at the first add
+// then the gathered values are summed, so that the L2 latency of the gathers hides behind independent
+// work.  Measured and rejected (profiles/r02_h_variants.txt): the 24 registers of gathered doubles
+// held across the movement code spill at the 72-register budget (18.2 vs 16.3 us per medium-central
+// step) and a 6-CTA budget loses as much in occupancy (18.6 us).
 #ifndef MBE_UPT_EARLY_MOVE
-#define MBE_UPT_EARLY_MOVE 1
+#define MBE_UPT_EARLY_MOVE 0
 #endif
 #ifndef MBE_UPT_LUT_HINT
 #define MBE_UPT_LUT_HINT 2  // read-only path for the rate table: measured -2.3% (multi-agent), neutral (central)

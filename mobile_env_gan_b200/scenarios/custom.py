@@ -20,7 +20,9 @@ class MComCustom(MComCore):
         config = super().default_config()
         config["ue"].update({"velocity": 10})
         config.update({"bs_random": cls.BS_RANGE, "max_bs": cls.BS_RANGE[1], "mode": "fork",
-                       "shared_trajectory": "follow_movement"})
+                       "shared_trajectory": "follow_movement",
+                       # one env = the reference's own use (collectData2.ipynb): step() dumps like base.py:261
+                       "dumps": None})
         return config
 
     def __init__(self, config=None, render_mode=None):

@@ -229,3 +229,65 @@ def test_formatters_reproduce_the_shipped_collect_loop_files():
             e, rec["bs_xy"], [st["pos"] for st in steps], [st["arrived"] for st in steps],
             [st["assoc"] for st in steps], [st["rate"] for st in steps], util), root)
     assert n == 168
+
+
+@pytest.mark.gpu
+def test_collect_notebook_loop_runs_verbatim(tmp_path, monkeypatch):
+    """collectData2.ipynb cells 2-4 as written in the reference (env = MComCustom(render_mode="rgb_array");
+    per epoch reset / save_base_station_positions / 20 x step(epoch, step) / save_epoch_data): the env-level
+    methods of base.py:261,298-404 and custom.py:79-85 write into ../collectData and ../collectData2
+    relative to the working directory, and the files are the ones export.ReferenceDumpWriter writes for an
+    identical env (which other tests pin to the reference's own files)."""
+    from mobile_env_gan_b200.export import ReferenceDumpWriter
+    from mobile_env_gan_b200.scenarios.custom import MComCustom
+
+    work = tmp_path / "run" / "notebooks"
+    work.mkdir(parents=True)
+    monkeypatch.chdir(work)
+
+    env = MComCustom(render_mode="rgb_array")
+    iteration_number = 2
+    step_number = 20
+    env.reset()
+    for epoch_number in range(iteration_number):
+        env.reset()
+        env.save_base_station_positions(epoch_number)
+
+        for curr_step in range(step_number):
+            env.step(epoch_number, curr_step)
+
+        env.save_epoch_data(epoch_number)
+
+    # the reference's bookkeeping attributes (base.py:264-269) and the monitor call of base.py:272
+    assert sorted(env.users_dataRateList) == list(range(7)) and len(env.users_dataRateList[0]) == step_number
+    assert len(env.users_trajectoryList[3]) == step_number and len(env.userQoEList[6]) == step_number
+    assert len(env.monitor.scalar_results["mean utility"]) == step_number
+    assert set(env.monitor.info()) >= {"number connections", "number connected", "mean utility", "mean datarate"}
+
+    def tree(root):
+        out = {}
+        for dirpath, _, names in os.walk(root):
+            for name in names:
+                full = os.path.join(dirpath, name)
+                out[os.path.relpath(full, root)] = open(full).read()
+        return out
+
+    got = tree(tmp_path / "run")
+    got = {rel: text for rel, text in got.items() if rel.startswith("collectData")}
+    assert len(got) == iteration_number * 84
+
+    twin = MComCustom(config={"dumps": False})
+    twin.reset()
+    for epoch_number in range(iteration_number):
+        twin.reset()
+        writer = ReferenceDumpWriter(twin, str(tmp_path / "twin"), envs=[0], epoch_offset=epoch_number)
+        writer.begin_episode()
+        for curr_step in range(step_number):
+            twin.step(epoch_number, curr_step)
+            writer.after_step(curr_step)
+        writer.end_episode()
+        writer.close()
+    assert got == tree(tmp_path / "twin")
+    # a batch keeps the fast path: no dumps, no per-step monitor clones unless asked for
+    batch = MComCustom(config={"num_envs": 64})
+    assert not batch.dumps and not batch.monitor_in_step

@@ -507,9 +507,9 @@ def test_readme_pathloss_example_runs_verbatim_and_matches_the_oracle():
 @pytest.mark.parametrize("wire", ["compact", "raw"])
 @pytest.mark.parametrize("handler", ["central", "ma"])
 def test_step_host_wire_formats_reproduce_the_device_observation(wire, handler, monkeypatch):
-    """mbe_step_host ships observations in the compact wire format (mask bits + snr ratios + utility,
-    per-env BS utilities for the multi-agent handler) and expands them with host threads -- or, with
-    MBE_HOST_WIRE=raw, as plain FP32 rows by DMA.  Either way obs_host must equal the device tensor bit
+    """mbe_step_host ships observations as plain FP32 rows by DMA (the default) or, with
+    MBE_HOST_WIRE=compact, in the compact wire format (mask bits + snr ratios + utility, per-env BS
+    utilities for the multi-agent handler) expanded by host threads.  Either way obs_host must equal the device tensor bit
     for bit, including the all-zero rows of finished episodes (no autoreset) and fresh rows after a reset."""
     import mobile_env_gan_b200 as mbe
 
@@ -535,9 +535,11 @@ def test_step_host_wire_formats_reproduce_the_device_observation(wire, handler, 
     assert bool((env.obs.view(E, -1).abs().sum(dim=1) == 0).any())  # inactive envs were part of the comparison
 
 
-def test_step_host_compact_wire_on_a_wide_shape():
+def test_step_host_compact_wire_on_a_wide_shape(monkeypatch):
     """Two mask words per UE (40 BSs), multi-agent, block-per-env kernel, env windows."""
     from test_gpu_parity import wide_env
+
+    monkeypatch.setenv("MBE_HOST_WIRE", "compact")
 
     env, B, U = wide_env("wide_pf", "gym", "ma", 800, autoreset=True)
     env.reset()
