@@ -94,6 +94,7 @@ struct mbe_env {
   void (*tpe)(mbe::StepArgs) = nullptr;
   size_t tpe_smem = 0;
   bool tpe_bound_ok = false;
+  bool tpe_shared = false;                       // the fused episode of a shared layout (no per-env BS table)
   void (*tpe_rollout)(mbe::StepArgs) = nullptr;  // the same kernel looping over the steps of an episode
   size_t tpe_rollout_smem = 0;
   // mbe_step_host pipeline: second stream + fork/join events (created on first use)
@@ -433,6 +434,27 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
       env->tpe_rollout = mbe::step_tpe_fork_kernel<7, 10, true>;
       env->tpe_rollout_smem = sizeof(mbe::TpeRolloutSmem<7, 10>);
     }
+    // the scenario shapes in FORK mode (one layout shared by all envs): the fused episode only (5 x 3 and
+    // 15 x 4); their single step stays on the warp-segment kernel
+    if (on && !gym && !a.bs_per_env && spec_ok && cfg->num_classes == 1 && !env->big && a.E % 32 == 0 &&
+        cfg->width <= 2048 && cfg->height <= 2048 && !(cfg->flags & MBE_FLAG_GENERIC_KERNEL)) {
+      env->tpe_shared = true;
+      if (a.U == 5 && a.B == 3) {
+        env->tpe_rollout = mbe::step_tpe_fork_kernel<5, 3, true, true>;
+        env->tpe_rollout_smem = sizeof(mbe::TpeRolloutSmem<5, 3>);
+      } else if (a.U == 15 && a.B == 4) {
+        env->tpe_rollout = mbe::step_tpe_fork_kernel<15, 4, true, true>;
+        env->tpe_rollout_smem = sizeof(mbe::TpeRolloutSmem<15, 4>);
+      } else if (a.U == 30 && a.B == 13 && std::getenv("MBE_TPE_LARGE") && std::getenv("MBE_TPE_LARGE")[0] == '1') {
+        // opt-in: one env per lane walks 30 x 13 pairs in scalar code at 208 registers -- 1.43 ms per
+        // 20-step episode of 65,536 envs against 0.83 ms for 20 launches of the warp-segment kernel
+        // (profiles/r02_j_fork_rollout.txt); the small and medium shapes win 7.1x and 1.8x
+        env->tpe_rollout = mbe::step_tpe_fork_kernel<30, 13, true, true>;
+        env->tpe_rollout_smem = sizeof(mbe::TpeRolloutSmem<30, 13>);
+      } else {
+        env->tpe_shared = false;
+      }
+    }
   }
   if (env->big && std::floor(cfg->width) * std::floor(cfg->width) + std::floor(cfg->height) * std::floor(cfg->height) >=
                       16777216.0) {
@@ -562,6 +584,11 @@ int mbe_bind(mbe_env* env, const mbe_buffers* b) {
                     (uintptr_t)b->utility | (uintptr_t)b->done | (uintptr_t)b->metrics;
     // bulk async copies need 16-byte aligned global addresses; the FORK thread-per-env kernel also needs nbs
     env->tpe_bound_ok = (all & 15) == 0 && b->nbs != nullptr;
+    if (env->tpe_shared) {
+      all = (uintptr_t)b->pos | (uintptr_t)b->wp | (uintptr_t)b->t | (uintptr_t)b->episode | (uintptr_t)b->assoc |
+            (uintptr_t)b->rate | (uintptr_t)b->utility | (uintptr_t)b->done | (uintptr_t)b->metrics;
+      env->tpe_bound_ok = (all & 15) == 0;
+    }
     uintptr_t pf = (uintptr_t)b->pos | (uintptr_t)b->wp | (uintptr_t)b->conn | (uintptr_t)b->actions;
     env->pf_bound_ok = (pf & 15) == 0;
   }
@@ -780,14 +807,15 @@ int mbe_rollout(mbe_env* env, int steps, float* qoe_acc, float threshold, const 
     a.ro_assoc = o.assoc;
     a.ro_rate = o.rate;
     a.ro_util = o.utility;
-    mbe::step_tpe_fork_kernel<7, 10, true><<<a.E / 32, 32, env->tpe_rollout_smem, st>>>(a);
+    env->tpe_rollout<<<a.E / 32, 32, env->tpe_rollout_smem, st>>>(a);
     MBE_CUDA(cudaGetLastError());
     env->launches += 1;
     return 0;
   }
   // other shapes: the same episode as a sequence of step launches
   if ((o.pos || o.wp) && env->cfg.autoreset)
-    return fail("mbe_rollout: per-step positions with autoreset need the fused kernel (7 UEs, 10 BS slots, per-env layouts)");
+    return fail("mbe_rollout: per-step positions with autoreset need the fused kernel (MComCustom's 7 UEs x 10 BS slots "
+                "or a scenario shape, num_envs a multiple of 32)");
   if (o.rate && !a0.rate) return fail("mbe_rollout: a rate series needs the rate buffer bound");
   for (int s = 0; s < steps; ++s) {
     if (int rc = launch(env, mbe::OP_STEP, MBE_PHASE_ALL, nullptr, stream)) return rc;

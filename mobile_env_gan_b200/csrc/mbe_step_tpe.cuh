@@ -14,7 +14,9 @@
 // per launch; optional per-step outputs (positions after the move, association, rate, QoE:
 // the series behind base.py:298-404's dumps) leave as bulk stores [T,E,U], and the QoE statistics
 // of the layout score (qoe_accumulate_kernel, mbe_step.cuh) accumulate in registers.
-// Preconditions (dispatcher): FORK mode, per-env layout, one BS class, E % 32 == 0, exact-FP32
+// SHARED = true is the same kernel for a layout shared by all envs (the scenario shapes in FORK mode):
+// the BS terms come from the kernel parameters, there is no per-env BS table to load, regenerate or store.
+// Preconditions (dispatcher): FORK mode, per-env layout (or SHARED), one BS class, E % 32 == 0, exact-FP32
 // map no larger than 2048 x 2048 (the packed nearest-BS key must not overflow), no debug SNR buffer, all stream
 // bases 16-byte aligned, nbs bound.
 #pragma once
@@ -90,11 +92,43 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
 #define MBE_TPE_ROLLOUT_BLOCKS 16
 #endif
 
-template <int U, int B, bool ROLLOUT = false>
-__global__ void __launch_bounds__(32, ROLLOUT ? MBE_TPE_ROLLOUT_BLOCKS : MBE_TPE_BLOCKS) step_tpe_fork_kernel(const __grid_constant__ StepArgs a) {
+// |connections(b)| of one env, packed into 64-bit words: 4 bits per BS while a count cannot exceed 15,
+// else 8 bits (two words for more than 8 BSs)
+template <int U, int B>
+struct TpeCounts {
+  static constexpr int kBits = U <= 15 ? 4 : 8;
+  static constexpr int kPer = 64 / kBits;
+  static constexpr int kWords = (B + kPer - 1) / kPer;
+  unsigned long long w[kWords];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < kWords; ++i) w[i] = 0ull;
+  }
+  __device__ __forceinline__ void add(int b) {
+    if (kWords == 1) {
+      w[0] += 1ull << (kBits * b);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kWords; ++i)
+        if (b / kPer == i) w[i] += 1ull << (kBits * (b % kPer));
+    }
+  }
+  __device__ __forceinline__ unsigned get(int b) const {
+    unsigned long long v = w[0];
+    if (kWords > 1) {
+#pragma unroll
+      for (int i = 1; i < kWords; ++i)
+        if (b / kPer == i) v = w[i];
+    }
+    return (unsigned)(v >> (kBits * (b % kPer))) & ((1u << kBits) - 1u);
+  }
+};
+
+template <int U, int B, bool ROLLOUT = false, bool SHARED = false>
+__global__ void __launch_bounds__(32, ROLLOUT ? (U > 16 ? 8 : MBE_TPE_ROLLOUT_BLOCKS) : MBE_TPE_BLOCKS) step_tpe_fork_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using S = typename std::conditional<ROLLOUT, TpeRolloutSmem<U, B>, TpeForkSmem<U, B>>::type;
-  static_assert(B <= 16, "per-BS counts are packed 4 bits per BS into 64 bits");
+  static_assert(B <= 16, "the nearest-BS key keeps the BS index in 4 bits");
   static_assert(U <= 32, "the QoE tree replays a 32-lane reduction");
   S& s = *reinterpret_cast<S*>(smem_raw);
   const int lane = threadIdx.x;
@@ -111,11 +145,13 @@ __global__ void __launch_bounds__(32, ROLLOUT ? MBE_TPE_ROLLOUT_BLOCKS : MBE_TPE
   if (lane == 0) {
     mbar_init(&s.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(&s.bar, 2 * EU + EB + 3 * EE);
+    mbar_expect_tx(&s.bar, 2 * EU + (SHARED ? 0u : EB + EE) + 2 * EE);
     bulk_load(s.pos, a.pos + e0 * U, EU, &s.bar);
     bulk_load(s.wp, a.wp + e0 * U, EU, &s.bar);
-    bulk_load(s.bs, a.bs_xy + e0 * B, EB, &s.bar);
-    bulk_load(s.nbs, a.nbs + e0, EE, &s.bar);
+    if (!SHARED) {
+      bulk_load(s.bs, a.bs_xy + e0 * B, EB, &s.bar);
+      bulk_load(s.nbs, a.nbs + e0, EE, &s.bar);
+    }
     bulk_load(s.t, a.t + e0, EE, &s.bar);
     bulk_load(s.epi, a.episode + e0, EE, &s.bar);
   }
@@ -125,7 +161,7 @@ __global__ void __launch_bounds__(32, ROLLOUT ? MBE_TPE_ROLLOUT_BLOCKS : MBE_TPE
   uint32_t* my_pos = s.pos + lane * U;
   uint32_t* my_wp = s.wp + lane * U;
   uint32_t* my_bs = s.bs + lane * B;
-  int t_e = s.t[lane], epi = s.epi[lane], nb = s.nbs[lane];
+  int t_e = s.t[lane], epi = s.epi[lane], nb = SHARED ? B : s.nbs[lane];
 
   float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   if (ROLLOUT && a.qoe_acc) acc = a.qoe_acc[env];
@@ -144,8 +180,12 @@ __global__ void __launch_bounds__(32, ROLLOUT ? MBE_TPE_ROLLOUT_BLOCKS : MBE_TPE
 #pragma unroll
   for (int b = 0; b < B; ++b) {
     int bx, by;
-    unpack_xy(my_bs[b], bx, by);
-    if (b >= nb) bx = by = -6000;  // 2*(6000+2048)^2 << 4 still fits int32; > any d2max on such a map
+    if (SHARED) {
+      bx = a.slot[b].x, by = a.slot[b].y;
+    } else {
+      unpack_xy(my_bs[b], bx, by);
+      if (b >= nb) bx = by = -6000;  // 2*(6000+2048)^2 << 4 still fits int32; > any d2max on such a map
+    }
     cb[b] = ((bx * bx + by * by) << 4) | b;
     mx[b] = -32 * bx;
     my[b] = -32 * by;
@@ -166,7 +206,8 @@ __global__ void __launch_bounds__(32, ROLLOUT ? MBE_TPE_ROLLOUT_BLOCKS : MBE_TPE
 
   // ---- move (movement.py:42-62), then nearest connectable BS (base.py:236-241) ----
   int best[U], bestd2[U];
-  unsigned long long packed = 0ull;  // |connections(b)|, 4 bits per BS
+  TpeCounts<U, B> packed;  // |connections(b)|
+  packed.clear();
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     int x, y, wx, wy;
@@ -189,7 +230,7 @@ __global__ void __launch_bounds__(32, ROLLOUT ? MBE_TPE_ROLLOUT_BLOCKS : MBE_TPE
     const int bb = (bd <= C0.d2max) ? (key & 15) : -1;
     best[u] = bb;
     bestd2[u] = bd;
-    if (bb >= 0) packed += 1ull << (4 * bb);
+    if (bb >= 0) packed.add(bb);
   }
 
   // ---- ResourceFair split + rounding (schedules.py:20-22, base.py:435), utility (253-258) ----
@@ -201,7 +242,7 @@ __global__ void __launch_bounds__(32, ROLLOUT ? MBE_TPE_ROLLOUT_BLOCKS : MBE_TPE
   for (int u = 0; u < U; ++u) {
     double rate = 0.0;
     if (best[u] >= 0) {
-      const unsigned n = (unsigned)(packed >> (4 * best[u])) & 15u;
+      const unsigned n = packed.get(best[u]);
       rate = lut[n * stride + (unsigned)bestd2[u]];
       nconn += 1;
     }
@@ -244,7 +285,7 @@ __global__ void __launch_bounds__(32, ROLLOUT ? MBE_TPE_ROLLOUT_BLOCKS : MBE_TPE
       my_wp[u] = pack_xy(-1, -1);
       if (a.inj_wp) a.wp_cnt[(size_t)env * U + u] = 0;
     }
-    if (a.bs_rand_max > 0) {  // generate_base_stations (custom.py:68-77)
+    if (!SHARED && a.bs_rand_max > 0) {  // generate_base_stations (custom.py:68-77)
       nb = philox_bs_count(a, gid, (unsigned)epi);
 #pragma unroll 1
       for (int b = 0; b < B; ++b) {
@@ -256,7 +297,7 @@ __global__ void __launch_bounds__(32, ROLLOUT ? MBE_TPE_ROLLOUT_BLOCKS : MBE_TPE
   }
   s.t[lane] = t_e;
   s.epi[lane] = epi;
-  s.nbs[lane] = nb;
+  if (!SHARED) s.nbs[lane] = nb;
 
   if constexpr (ROLLOUT) if (ro_out) {  // per-step series [T,E,U]
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -287,7 +328,7 @@ __global__ void __launch_bounds__(32, ROLLOUT ? MBE_TPE_ROLLOUT_BLOCKS : MBE_TPE
     bulk_store(a.done + e0, s.done, 32);
     bulk_store(a.t + e0, s.t, EE);
     bulk_store(a.episode + e0, s.epi, EE);
-    if (a.bs_rand_max > 0) {
+    if (!SHARED && a.bs_rand_max > 0) {
       bulk_store(a.bs_xy + e0 * B, s.bs, EB);
       bulk_store(a.nbs + e0, s.nbs, EE);
     }

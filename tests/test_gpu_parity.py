@@ -916,6 +916,43 @@ def test_rollout_positions_on_reset_steps_are_the_moved_ones():
     assert int(a.episode.min()) == 1 and int(a.t.max()) == 0
 
 
+@pytest.mark.parametrize("size,autoreset,steps", [("small", True, 47), ("medium", True, 47), ("medium", False, 20),
+                                                  ("large", True, 23)])
+def test_fused_rollout_equals_stepping_scenario_shapes(size, autoreset, steps, monkeypatch):
+    """The fused episode for the scenario shapes in FORK mode (one BS layout shared by all envs:
+    step_tpe_fork_kernel<U,B,ROLLOUT,SHARED>; 8-bit per-BS counts for 30 UEs): one launch against the
+    same number of mbe_step + mbe_accumulate_qoe calls on the warp-segment kernel -- final state, score
+    statistics and per-step series bit-identical."""
+    from mobile_env_gan_b200.scenarios import MComLarge, MComMedium, MComSmall
+    from mobile_env_gan_b200.scoring import LayoutScorer
+
+    cls = {"small": MComSmall, "medium": MComMedium, "large": MComLarge}[size]
+    monkeypatch.setenv("MBE_TPE_LARGE", "1")  # 30 x 13 is opt-in (slower than stepping), still bit-identical
+    E = 2048
+    cfg = {"num_envs": E, "autoreset": autoreset, "mode": "fork", "ue": {"velocity": 7.5}}
+    a, b = cls(config=dict(cfg)), cls(config=dict(cfg))
+    sa, sb = LayoutScorer(a, 0.1), LayoutScorer(b, 0.1)
+    a.reset(), b.reset()
+    a.step(0, 0), b.step(0, 0)  # start mid-episode
+    sa.acc.fill_(0.25), sb.acc.fill_(0.25)
+    before = a.launch_count
+    series = sa.run_episode(steps, record=("pos", "wp", "assoc", "rate", "utility"))
+    assert a.launch_count - before == 1
+    for k in range(steps):
+        b.step(0, k)
+        sb.update()
+        torch.cuda.synchronize()
+        assert torch.equal(series["assoc"][k], b.assoc), k
+        assert torch.equal(series["rate"][k], b.rate), k
+        assert torch.equal(series["utility"][k], b.utility_scaled), k
+        if not (autoreset and bool(b.done.any())):
+            assert torch.equal(series["pos"][k], b.pos) and torch.equal(series["wp"][k], b.wp), k
+    for name in ("pos", "wp", "t", "episode", "assoc", "rate", "utility_scaled", "metrics", "done"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert torch.equal(sa.acc, sb.acc)
+    assert int(b.assoc.max()) >= 0 and len(torch.unique(b.assoc)) > 2  # several BSs really serve UEs
+
+
 def test_rollout_other_shapes_run_as_step_sequence():
     """Shapes without the fused kernel: same API, same results, one launch per step."""
     from mobile_env_gan_b200.scoring import LayoutScorer
