@@ -206,6 +206,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mobile-medium-central-v0")
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU per batch")
+    ap.add_argument("--total-envs", type=int, default=0,
+                    help="strong scaling: this many envs per batch over ALL GPUs (envs per GPU = total / N)")
     ap.add_argument("--cpu-seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
@@ -217,6 +219,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.total_envs:
+        if args.total_envs % (32 * world):
+            ap.error("--total-envs must be a multiple of 32 x the number of GPUs")
+        args.envs = args.total_envs // world
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -484,7 +490,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if args.total_envs else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": make_config(args),
             "repeats": repeats,
             "timing": {"what": f"median of {repeats} timed blocks of K={args.steps} steps, each block bracketed by "
