@@ -18,6 +18,15 @@
 #include <type_traits>
 #include "mbe_device.cuh"
 
+// 1 = the central handler tests connectivity only for the connected BSs and the action's BS (experiment switch)
+#ifndef MBE_BIG_SPARSE_PRE
+#define MBE_BIG_SPARSE_PRE 1
+#endif
+// observation rows of a warp: 0 = a contiguous share of the rows, 1 = every 8th row (the CTA's warps write one
+// advancing window of 8 rows)
+#ifndef MBE_BIG_ROW_INTERLEAVE
+#define MBE_BIG_ROW_INTERLEAVE 0
+#endif
 #ifndef MBE_BIG_MIN_BLOCKS
 #define MBE_BIG_MIN_BLOCKS 3
 #endif
@@ -82,8 +91,11 @@ __device__ __forceinline__ double link_share(const StepArgs& a, const ClassDev& 
   return rint(share * 100.0) / 100.0;
 }
 
-template <int MODE, int HANDLER>
-__global__ void __launch_bounds__(kBigThreads, MBE_BIG_MIN_BLOCKS) step_big_kernel(const __grid_constant__ StepArgs a) {
+// MAXI = UEs per thread held in registers (U <= MAXI * 256): 2 covers the synthetic 512-UE shape with 64
+// registers and 4 resident CTAs per SM, 4 (U <= 1024) needs 80 registers / 3 CTAs
+template <int MODE, int HANDLER, int MAXI = kBigMaxI>
+__global__ void __launch_bounds__(kBigThreads, MAXI <= 2 ? MBE_BIG_MIN_BLOCKS + 1 : MBE_BIG_MIN_BLOCKS) step_big_kernel(const __grid_constant__ StepArgs a) {
+  constexpr int kBigMaxI = MAXI;  // shadows the namespace constant inside this kernel
   constexpr bool GYM = (MODE == 1);
   constexpr bool MA = (HANDLER == 1);
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -262,6 +274,25 @@ __global__ void __launch_bounds__(kBigThreads, MBE_BIG_MIN_BLOCKS) step_big_kern
       const size_t idx = (size_t)env * U + u;
       const float xf = (float)x[i], yf = (float)y[i];
       float bestf = 3.0e38f;
+      int act = 0;
+      if (GYM) act = a.actions[idx];
+      if (MBE_BIG_SPARSE_PRE && GYM && !MA && !a.dbg_snr) {
+        // The central handler only ever asks "is BS b connectable" for the BSs the UE is connected to
+        // (update_connections, base.py:221-227) and for the BS its action names: test those few pairs
+        // instead of all B (the multi-agent reward and the FORK association need every pair).  Only
+        // the tested bits of e0 / e1 are meaningful afterwards, and only those are read below.
+        const int ab = (act > 0 && act <= nb) ? act - 1 : -1;
+        for (int w = 0; w < 2; ++w) {
+          uint32_t m = (w ? c1[i] : c0[i]) | ((ab >= 32 * w && ab < 32 * w + 32) ? 1u << (ab & 31) : 0u);
+          uint32_t ew = 0;
+          while (m) {
+            const int bl = __ffs(m) - 1, b = bl + 32 * w;
+            m &= m - 1;
+            if (d2f_to(xf, yf, b) <= (one_class ? d2max0f : (float)link(i, b).d2max)) ew |= 1u << bl;
+          }
+          if (w) e1[i] = ew; else e0[i] = ew;
+        }
+      } else
       for (int w = 0; w < 2; ++w) {  // one 32-bit mask word at a time (no per-BS word select)
         uint32_t ew = 0;
         const int b_lo = 32 * w, b_hi = min(nb, 32 * w + 32);
@@ -281,7 +312,6 @@ __global__ void __launch_bounds__(kBigThreads, MBE_BIG_MIN_BLOCKS) step_big_kern
       if (GYM) {
         c0[i] &= e0[i];  // update_connections (base.py:221-227)
         c1[i] &= e1[i];
-        const int act = a.actions[idx];
         if (act > 0 && act <= nb) {  // NOOP_ACTION = 0 (base.py:29)
           const int b = act - 1;
           uint32_t& cw = (b < 32) ? c0[i] : c1[i];
@@ -440,11 +470,21 @@ __global__ void __launch_bounds__(kBigThreads, MBE_BIG_MIN_BLOCKS) step_big_kern
     }
     __syncthreads();
 
+#if MBE_BIG_ROW_INTERLEAVE
+    const int rstep = kBigWarps;
+    const int r0 = warp, r1 = U;
+#else
+    const int rstep = 1;
     const int rpw = (U + kBigWarps - 1) / kBigWarps;  // rows per warp (contiguous: write locality)
     const int r0 = warp * rpw, r1 = min(U, r0 + rpw);
+#endif
     float* obase = a.obs + (size_t)env * U * F;
     if (done && !fresh) {  // inactive UEs observe zeros
+#if MBE_BIG_ROW_INTERLEAVE
+      for (size_t e = (size_t)tid; e < (size_t)U * F; e += kBigThreads) obase[e] = 0.0f;
+#else
       for (size_t e = (size_t)r0 * F + lane; e < (size_t)r1 * F; e += 32) obase[e] = 0.0f;
+#endif
       return;
     }
     const int b0 = lane, b1 = lane + 32;
@@ -465,7 +505,7 @@ __global__ void __launch_bounds__(kBigThreads, MBE_BIG_MIN_BLOCKS) step_big_kern
       constexpr bool FULL = decltype(full_tag)::value;
       const int BB = FULL ? 64 : B;
 #pragma unroll 2
-      for (int u = r0; u < r1; ++u) {
+      for (int u = r0; u < r1; u += rstep) {
         const float2 p = s.pxy[u];
         const uint2 cw = s.cw[u];
         float* row = obase + (size_t)u * F;
@@ -522,7 +562,7 @@ __global__ void __launch_bounds__(kBigThreads, MBE_BIG_MIN_BLOCKS) step_big_kern
     else rows(std::false_type{});
     // the utility column (one element per row, stride F): 32 rows per store instruction instead of a
     // predicated single-lane store in every row
-    for (int u = r0 + lane; u < r1; u += 32) obase[(size_t)u * F + 2 * B] = s.ut[u];
+    for (int u = r0 + lane * rstep; u < r1; u += 32 * rstep) obase[(size_t)u * F + 2 * B] = s.ut[u];
   };
 
   // ================= run =================
