@@ -1,6 +1,8 @@
 """Arrival plugins (reference mobile_env/core/arrival.py)."""
 from __future__ import annotations
 
+import numpy as np
+
 
 class Arrival:
     kernel_id = None
@@ -9,9 +11,17 @@ class Arrival:
         self.ep_time = ep_time
         self.seed = seed
         self.reset_rng_episode = reset_rng_episode
+        self.rng = None
 
     def reset(self) -> None:
-        pass
+        if self.reset_rng_episode or self.rng is None:  # arrival.py:14-16
+            self.rng = np.random.default_rng(self.seed)
+
+    def setArrivalTime(self, ue) -> int:
+        raise NotImplementedError
+
+    def setDepartureTime(self, ue) -> int:
+        raise NotImplementedError
 
 
 class NoDeparture(Arrival):

@@ -414,3 +414,38 @@ def test_reference_install_runs_the_unmodified_step(tmp_path):
     finally:
         os.chdir(cwd)
     assert steps >= 8
+
+
+def test_scalar_movement_plugin_methods_match_the_reference_class():
+    """Movement.reset / initial_position / move -- the per-entity plugin methods the reference env calls
+    (base.py:189, 199, 233; movement.py:16-18, 42-72): same PCG64 stream, same positions, same bookkeeping
+    dictionaries as the reference's RandomWaypointMovement for three UEs over 120 moves and a reset."""
+    from oracle import ref_harness
+
+    if not ref_harness.reference_available():
+        pytest.skip("the reference is only importable in the build container")
+    ref_harness.import_reference()
+    from mobile_env.core.entities import UserEquipment as RefUE
+    from mobile_env.core.movement import RandomWaypointMovement as RefMove
+
+    from mobile_env_gan_b200.core.entities import UserEquipment
+    from mobile_env_gan_b200.core.movement import RandomWaypointMovement
+
+    for reset_rng in (True, False):
+        kw = dict(width=200, height=160, seed=2028, reset_rng_episode=reset_rng)
+        mine, ref = RandomWaypointMovement(**kw), RefMove(**kw)
+        ues = [UserEquipment(i, velocity=v, snr_tr=2e-8, noise=1e-9, height=1.5) for i, v in enumerate((1.5, 10, 37.5))]
+        rues = [RefUE(i, velocity=v, snr_tr=2e-8, noise=1e-9, height=1.5) for i, v in enumerate((1.5, 10, 37.5))]
+        for episode in range(2):
+            mine.reset(), ref.reset()
+            for a, b in zip(ues, rues):
+                a.x, a.y = mine.initial_position(a)
+                b.x, b.y = ref.initial_position(b)
+                assert (a.x, a.y) == (b.x, b.y) and mine.initial_position(a) == (a.x, a.y)
+            for _ in range(60):
+                for a, b in zip(ues, rues):
+                    a.x, a.y = mine.move(a)
+                    b.x, b.y = ref.move(b)
+                    assert (int(a.x), int(a.y)) == (int(b.x), int(b.y))
+                assert {u.ue_id: w for u, w in mine.userMoveDirection.items()} == \
+                       {u.ue_id: w for u, w in ref.userMoveDirection.items()}
