@@ -41,6 +41,7 @@ def load():
         _lib = C.CDLL(build())
         _lib.mbo_fork_step.restype = None
         _lib.mbo_gym_step.restype = None
+        _lib.mbo_set_tables.restype = None
     return _lib
 
 
@@ -52,7 +53,7 @@ class CEnvBatch:
     """E independent envs stepped by the C library.  ``p``: oracle.mbe_oracle.Params; ``bs_over``: per-BS
     overrides like the fixtures hold (keys bw / freq / tx / bs_height)."""
 
-    def __init__(self, p, bs_xy, num_envs, num_ues, handler="central", bs_over=None, nbs=None):
+    def __init__(self, p, bs_xy, num_envs, num_ues, handler="central", bs_over=None, nbs=None, pinned_tables=False):
         sched = {"resource_fair": 0, "proportional_fair": 1, "rate_fair": 2}[p.scheduler]
         self.lib = load()
         bs_xy = np.asarray(bs_xy, dtype=np.int32)
@@ -85,6 +86,42 @@ class CEnvBatch:
         self.metrics = np.zeros((E, 4), dtype=np.float64)
         self.bs_util = np.zeros((E, B), dtype=np.float64)
         self.obs = np.zeros((E, U, self.F), dtype=np.float32)
+        self.tables = None
+        if pinned_tables:
+            self.tables = self._numpy_tables(p, bs_over)
+
+    def _numpy_tables(self, p, bs_over):
+        """snr / Shannon rate per integer squared distance through the numpy scalar chain of
+        oracle/mbe_oracle.py (the reference's operation order: power_loss -> calculateSNR -> datarate,
+        channels.py:132-146, 24-27, 78-83), one table per BS parameter set.  With them the C steps return the
+        numpy rates bit for bit (see mbo_set_tables in the C file)."""
+        import dataclasses
+        import math
+
+        from oracle import mbe_oracle as orc
+
+        tab_len = int(p.width) ** 2 + int(p.height) ** 2 + 1
+        sets = [dict(o or {}) for o in (bs_over or [])] if any(bs_over or []) else [{}]
+        n_tabs = len(sets) if len(sets) > 1 else 1
+        if n_tabs > 1:
+            assert n_tabs == self.B
+        snr = np.zeros((n_tabs, tab_len), dtype=np.float64)
+        rate = np.zeros((n_tabs, tab_len), dtype=np.float64)
+        with np.errstate(divide="ignore", over="ignore"):
+            for i in range(n_tabs):
+                pp = dataclasses.replace(p, **sets[i]) if sets[i] else p
+                for d2 in range(tab_len):
+                    s_ = orc.snr_of(pp, math.sqrt(d2))
+                    snr[i, d2] = s_
+                    rate[i, d2] = orc.datarate_of(pp, s_)
+        return np.ascontiguousarray(snr), np.ascontiguousarray(rate), n_tabs, tab_len
+
+    def _tables_on(self):
+        if self.tables is None:
+            self.lib.mbo_set_tables(None, None, 0, 0)
+        else:
+            snr, rate, n_tabs, tab_len = self.tables
+            self.lib.mbo_set_tables(_p(snr, C.c_double), _p(rate, C.c_double), n_tabs, tab_len)
 
     def reset(self, init_pos):
         self.pos[:] = np.asarray(init_pos, dtype=np.int32)
@@ -94,6 +131,7 @@ class CEnvBatch:
 
     def step_fork(self, new_wp):
         new_wp = np.ascontiguousarray(np.broadcast_to(np.asarray(new_wp, dtype=np.int32), self.pos.shape))
+        self._tables_on()
         self.lib.mbo_fork_step(C.byref(self.cp), self.E, self.U, self.B, _p(self.bs_par, C.c_double),
                                _p(self.bs_xy, C.c_int32), int(self.per_env), _p(self.nbs, C.c_int32),
                                _p(self.pos, C.c_int32), _p(self.wp, C.c_int32), _p(new_wp, C.c_int32),
@@ -106,6 +144,7 @@ class CEnvBatch:
             raise NotImplementedError("GYM step of the C restatement: shared layouts only")
         new_wp = np.ascontiguousarray(np.broadcast_to(np.asarray(new_wp, dtype=np.int32), self.pos.shape))
         acts = np.ascontiguousarray(np.broadcast_to(np.asarray(actions, dtype=np.int32), (self.E, self.U)))
+        self._tables_on()
         self.lib.mbo_gym_step(C.byref(self.cp), self.E, self.U, self.B, _p(self.bs_par, C.c_double),
                               _p(self.bs_xy, C.c_int32), _p(self.pos, C.c_int32), _p(self.wp, C.c_int32),
                               _p(new_wp, C.c_int32), _p(self.drew, C.c_int32), _p(self.t, C.c_int32),

@@ -60,13 +60,33 @@ static void fold_bs(const mbo_params* p, const double* par /* bw, freq, tx, heig
   f->tx = par[2];
 }
 
-static inline double snr_at(const mbo_params* p, const bs_fold* f, int dx, int dy) {
-  const double dist = sqrt((double)(dx * dx + dy * dy));        /* bs.point.distance(ue.point) */
+/* Optional PINNED tables (mbo_set_tables): snr and Shannon rate per BS slot (or one shared table) and
+ * integer squared distance, computed by the caller with numpy in the reference's own operation order
+ * (oracle/mbe_oracle.py snr_of / datarate_of, which the golden vectors pin bit for bit).  glibc's
+ * log10 / pow / log2 may differ from numpy's in the last ulp; with the tables every rate this file
+ * produces is the numpy value exactly, so full-size comparisons can demand bit equality.  Without
+ * them the chain below runs on glibc (the independent restatement tests/test_c_oracle.py pins). */
+static const double* g_snr_tab = NULL;
+static const double* g_rate_tab = NULL;
+static int g_ntabs = 0, g_tablen = 0;
+void mbo_set_tables(const double* snr_tab, const double* rate_tab, int n_tabs, int tab_len) {
+  g_snr_tab = snr_tab;
+  g_rate_tab = rate_tab;
+  g_ntabs = n_tabs;
+  g_tablen = tab_len;
+}
+static inline size_t tab_index(int b, int d2) { return (size_t)(g_ntabs == 1 ? 0 : b) * (size_t)g_tablen + (size_t)d2; }
+
+static inline double snr_at(const mbo_params* p, const bs_fold* f, int b, int dx, int dy) {
+  const int d2 = dx * dx + dy * dy;
+  if (g_snr_tab && d2 < g_tablen) return g_snr_tab[tab_index(b, d2)];
+  const double dist = sqrt((double)d2);                         /* bs.point.distance(ue.point) */
   const double loss = f->tmp1 + f->tmp2 * log10(dist + 1e-16);  /* channels.py:146 */
   return pow(10.0, (f->tx - loss) / 10.0) / p->noise;           /* channels.py:26-27 */
 }
 
-static inline double datarate(const mbo_params* p, const bs_fold* f, double snr) {
+static inline double datarate(const mbo_params* p, const bs_fold* f, int b, int d2, double snr) {
+  if (g_rate_tab && d2 < g_tablen) return g_rate_tab[tab_index(b, d2)];
   return snr > p->snr_tr ? f->bw * log2(1.0 + snr) : 0.0; /* channels.py:80-83 */
 }
 
@@ -143,6 +163,7 @@ void mbo_fork_step(const mbo_params* p, int E, int U, int B, const double* bs_pa
     double* rt = rate + (size_t)e * U;
     double* ut = util + (size_t)e * U;
     double best_snr[MBO_MAX_U];
+    int best_d2[MBO_MAX_U];
     int cnt[MBO_MAX_B];
     memset(cnt, 0, sizeof(int) * (size_t)B);
     move_all(p, U, ps, wp + (size_t)e * U * 2, new_wp + (size_t)e * U * 2, drew ? drew + (size_t)e * U : NULL);
@@ -152,11 +173,12 @@ void mbo_fork_step(const mbo_params* p, int E, int U, int B, const double* bs_pa
         const int dx = ps[2 * u] - bs[2 * b], dy = ps[2 * u + 1] - bs[2 * b + 1];
         const int d2 = dx * dx + dy * dy;
         if (best >= 0 && d2 >= bestd2) continue; /* not nearer than the current choice: first minimum wins */
-        const double snr = snr_at(p, &fold[b], dx, dy);
+        const double snr = snr_at(p, &fold[b], b, dx, dy);
         if (snr > p->snr_tr) { /* check_connectivity, base.py:212-214 */
           best = b;
           bestd2 = d2;
           best_snr[u] = snr;
+          best_d2[u] = d2;
         }
       }
       as[u] = best;
@@ -168,12 +190,12 @@ void mbo_fork_step(const mbo_params* p, int E, int U, int B, const double* bs_pa
     if (p->scheduler) {
       memset(tot, 0, sizeof(fix_t) * (size_t)B);
       for (int u = 0; u < U; ++u)
-        if (as[u] >= 0) tot[as[u]] += sched_term(p->scheduler, datarate(p, &fold[as[u]], best_snr[u]));
+        if (as[u] >= 0) tot[as[u]] += sched_term(p->scheduler, datarate(p, &fold[as[u]], as[u], best_d2[u], best_snr[u]));
     }
     for (int u = 0; u < U; ++u) { /* base.py:421-435, 413-418, 253-258 */
       double r = 0.0;
       if (as[u] >= 0) {
-        r = 0.0 + round2(link_share(p->scheduler, datarate(p, &fold[as[u]], best_snr[u]), cnt[as[u]],
+        r = 0.0 + round2(link_share(p->scheduler, datarate(p, &fold[as[u]], as[u], best_d2[u], best_snr[u]), cnt[as[u]],
                                     p->scheduler ? tot[as[u]] : (fix_t)0));
         nconn += 1;
         rsum += r;
@@ -215,13 +237,16 @@ void mbo_gym_step(const mbo_params* p, int E, int U, int B, const double* bs_par
     double* rt = rate + (size_t)e * U;
     double* ut = util + (size_t)e * U;
     double* snr = (double*)malloc(sizeof(double) * (size_t)U * B);
+    int* d2s = (int*)malloc(sizeof(int) * (size_t)U * B);
     uint8_t* ok = (uint8_t*)malloc((size_t)U * B);
     int cnt[MBO_MAX_B];
     double bsu[MBO_MAX_B];
     for (int u = 0; u < U; ++u)
       for (int b = 0; b < B; ++b) {
-        const double s = snr_at(p, &fold[b], ps[2 * u] - bs_xy[2 * b], ps[2 * u + 1] - bs_xy[2 * b + 1]);
+        const int dx = ps[2 * u] - bs_xy[2 * b], dy = ps[2 * u + 1] - bs_xy[2 * b + 1];
+        const double s = snr_at(p, &fold[b], b, dx, dy);
         snr[u * B + b] = s;
+        d2s[u * B + b] = dx * dx + dy * dy;
         ok[u * B + b] = s > p->snr_tr;
       }
     /* (1) update_connections (base.py:221-227), (2) actions */
@@ -247,14 +272,14 @@ void mbo_gym_step(const mbo_params* p, int E, int U, int B, const double* bs_par
       tot[b] = 0;
       if (p->scheduler)
         for (int u = 0; u < U; ++u)
-          if (cn[u * B + b]) tot[b] += sched_term(p->scheduler, datarate(p, &fold[b], snr[u * B + b]));
+          if (cn[u * B + b]) tot[b] += sched_term(p->scheduler, datarate(p, &fold[b], b, d2s[u * B + b], snr[u * B + b]));
     }
     for (int u = 0; u < U; ++u) {
       double r = 0.0;
       int any = 0;
       for (int b = 0; b < B; ++b)
         if (cn[u * B + b]) {
-          r += round2(link_share(p->scheduler, datarate(p, &fold[b], snr[u * B + b]), cnt[b], tot[b]));
+          r += round2(link_share(p->scheduler, datarate(p, &fold[b], b, d2s[u * B + b], snr[u * B + b]), cnt[b], tot[b]));
           any = 1;
         }
       rt[u] = r;
@@ -308,7 +333,7 @@ void mbo_gym_step(const mbo_params* p, int E, int U, int B, const double* bs_par
         double s[MBO_MAX_B], mx = 0.0, tot = 0.0;
         uint8_t k[MBO_MAX_B];
         for (int b = 0; b < B; ++b) {
-          s[b] = snr_at(p, &fold[b], ps[2 * u] - bs_xy[2 * b], ps[2 * u + 1] - bs_xy[2 * b + 1]);
+          s[b] = snr_at(p, &fold[b], b, ps[2 * u] - bs_xy[2 * b], ps[2 * u + 1] - bs_xy[2 * b + 1]);
           k[b] = s[b] > p->snr_tr;
           if (b == 0 || s[b] > mx) mx = s[b];
           if (k[b]) tot += (double)cnt[b];
@@ -326,6 +351,7 @@ void mbo_gym_step(const mbo_params* p, int E, int U, int B, const double* bs_par
       }
     }
     free(snr);
+    free(d2s);
     free(ok);
   }
 }

@@ -172,3 +172,30 @@ def test_c_and_python_oracles_agree_on_random_fork_layouts(seed, U, v):
             np.testing.assert_allclose(c.rate[e], out["rate"], rtol=1e-12, atol=0)
             np.testing.assert_allclose(c.util[e], out["utility"], rtol=1e-12, atol=1e-15)
             assert bool(c.done[e]) == out["done"] and c.metrics[e][1] == out["n_connected"]
+
+
+@pytest.mark.parametrize("sched", ["resource_fair", "proportional_fair"])
+def test_pinned_tables_make_the_compiled_rates_the_numpy_rates(sched):
+    """``CEnvBatch(pinned_tables=True)`` feeds the C steps the snr / Shannon-rate tables of the numpy scalar
+    chain (oracle/mbe_oracle.py snr_of / datarate_of -- the reference's operation order, pinned by the golden
+    vectors); every FP64 rate of a 4,096-env GYM episode then equals the vectorised numpy oracle's bit for
+    bit, which is what lets the full-size GPU tests demand bit equality against the compiled restatement."""
+    from oracle.c_oracle import CEnvBatch
+
+    p = orc.Params(scheduler=sched)
+    bs = [(50, 50), (150, 50), (50, 150), (150, 150)]
+    E, U = 4096, 15
+    c = CEnvBatch(p, bs, E, U, handler="ma", pinned_tables=True)
+    rng = np.random.default_rng(5)
+    pos = rng.integers(0, 200, size=(E, U, 2))
+    c.reset(pos)
+    conn, wp, t = np.zeros((E, U, 4), dtype=bool), np.full((E, U, 2), -1), np.zeros(E, dtype=np.int64)
+    for k in range(20):
+        acts = rng.integers(0, 5, size=(E, U)).astype(np.int32)
+        new_wp = rng.integers(0, 200, size=(E, U, 2))
+        c.step_gym(acts, new_wp)
+        out = orc.batch_step_gym(p, pos, wp, new_wp, np.array(bs), conn, acts, t, handler="ma")
+        pos, wp, conn, t = out["pos"], out["wp"], out["conn"], out["t"]
+        assert np.array_equal(out["conn"], c.conn.astype(bool)) and np.array_equal(out["pos"], c.pos), k
+        assert np.array_equal(out["rate"], c.rate), (k, int((out["rate"] != c.rate).sum()))
+    assert float(c.rate.max()) > 0
