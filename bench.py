@@ -357,7 +357,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         block_ms = torch.tensor([a_.elapsed_time(b_) for a_, b_ in pairs], dtype=torch.float64, device=dev)
+        per_rank_median = None
         if world > 1:
+            # transparency: every rank's own median block (the reported time is the max over ranks per block)
+            mine = block_ms.median().reshape(1)
+            gathered = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine)
+            per_rank_median = [float(t_) for t_ in gathered]
             dist.all_reduce(block_ms, op=dist.ReduceOp.MAX)  # every block: max over ranks
         block_ms = sorted(float(v) for v in block_ms)
         ms = statistics.median(block_ms)
@@ -499,7 +505,8 @@ def main():
             "timing": {"what": f"median of {repeats} timed blocks of K={args.steps} steps, each block bracketed by "
                                "barrier + synchronize and taken as the max over ranks; CUDA events on the launching "
                                "stream behind a spin-kernel gate",
-                       "block_ms_min": block_ms[0], "block_ms_median": ms, "block_ms_max": block_ms[-1]},
+                       "block_ms_min": block_ms[0], "block_ms_median": ms, "block_ms_max": block_ms[-1],
+                       "per_rank_block_ms_median": per_rank_median},
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.workload),
