@@ -95,6 +95,7 @@ struct mbe_env {
   size_t tpe_smem = 0;
   bool tpe_bound_ok = false;
   void (*big_fn)(mbe::StepArgs) = nullptr;       // block-per-env kernel instance (UEs per thread by U)
+  size_t big_smem = 0;
   bool tpe_shared = false;                       // the fused episode of a shared layout (no per-env BS table)
   void (*tpe_rollout)(mbe::StepArgs) = nullptr;  // the same kernel looping over the steps of an episode
   size_t tpe_rollout_smem = 0;
@@ -475,18 +476,20 @@ int mbe_create(const mbe_config* cfg, mbe_env** out) {
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem);
   if (e == cudaSuccess && env->big) {
     // UEs per thread held in registers: 2 (64 registers, 4 CTAs per SM) up to 512 UEs, else 4
-// 0 = U <= 512 runs a 2-UEs-per-thread instance (64 registers, 4 CTAs per SM).  Measured slower than the
-// 4-UEs-per-thread instance at 80 registers / 3 CTAs (1105 vs 1046 us per 16,384-env synthetic step,
-// profiles/r02_q_variants.txt): more resident CTAs means more concurrent write streams, not more speed
+// 1 = always the 4-UEs-per-thread instance (80 registers, 3 CTAs per SM).  With the observation rows
+// leaving as aligned bulk tiles the 2-UEs-per-thread instance for U <= 512 (64 registers, 4 CTAs per SM,
+// smaller shared-memory arrays) is the faster one: 802 vs 920 us per 16,384-env synthetic step
+// (profiles/r02_zb_variants.txt); while the rows were direct 4-byte stores it was the slower one
+// (1105 vs 1046 us, r02_q): more resident CTAs only meant more contention on misaligned sectors
 #ifndef MBE_BIG_FORCE_MAXI4
-#define MBE_BIG_FORCE_MAXI4 1
+#define MBE_BIG_FORCE_MAXI4 0
 #endif
     const bool two = a.U <= 2 * mbe::kBigThreads && !MBE_BIG_FORCE_MAXI4;
     env->big_fn = gym ? (ma ? (two ? mbe::step_big_kernel<1, 1, 2> : mbe::step_big_kernel<1, 1, 4>)
                             : (two ? mbe::step_big_kernel<1, 0, 2> : mbe::step_big_kernel<1, 0, 4>))
                       : (two ? mbe::step_big_kernel<0, 0, 2> : mbe::step_big_kernel<0, 0, 4>);
-    e = cudaFuncSetAttribute((const void*)env->big_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(mbe::BigSmem));
+    env->big_smem = two ? mbe::big_smem_bytes<2>() : mbe::big_smem_bytes<4>();
+    e = cudaFuncSetAttribute((const void*)env->big_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->big_smem);
   }
   if (e == cudaSuccess && env->spec)
     e = cudaFuncSetAttribute((const void*)env->spec, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -665,7 +668,7 @@ static int launch(mbe_env* env, int op, int phases, const uint8_t* mask, void* s
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool gym = env->cfg.mode == MBE_MODE_GYM, ma = env->cfg.handler == MBE_HANDLER_MA;
   if (env->big) {
-    env->big_fn<<<grid, mbe::kBigThreads, sizeof(mbe::BigSmem), st>>>(a);
+    env->big_fn<<<grid, mbe::kBigThreads, env->big_smem, st>>>(a);
     MBE_CUDA(cudaGetLastError());
     env->launches += 1;
     return 0;

@@ -22,11 +22,6 @@
 #ifndef MBE_BIG_SPARSE_PRE
 #define MBE_BIG_SPARSE_PRE 1
 #endif
-// observation rows of a warp: 0 = a contiguous share of the rows, 1 = every 8th row (the CTA's warps write one
-// advancing window of 8 rows)
-#ifndef MBE_BIG_ROW_INTERLEAVE
-#define MBE_BIG_ROW_INTERLEAVE 0
-#endif
 #ifndef MBE_BIG_MIN_BLOCKS
 #define MBE_BIG_MIN_BLOCKS 3
 #endif
@@ -38,8 +33,15 @@ constexpr int kBigWarps = kBigThreads / 32;
 constexpr int kBigMaxI = 4;     // UEs per thread  => U <= 1024
 constexpr int kBigMaxU = kBigMaxI * kBigThreads;
 constexpr int kBigMaxB = 64;    // BS slots        => two 32-bit mask words
+// per-warp shared-memory tile of whole observation rows on their way out (floats): 8 rows of the 64-BS
+// central shape (8 x 129), 4 of the multi-agent one (4 x 257); 16-byte multiple
+#ifndef MBE_BIG_TILE_FLOATS
+#define MBE_BIG_TILE_FLOATS 1056
+#endif
+constexpr int kBigTileFloats = MBE_BIG_TILE_FLOATS;
 
-struct BigSmem {
+template <int MAXU>
+struct BigSmemT {
   float2 bsf[kBigMaxB];  // BS coordinates as floats (integers, exact)
   int cnt[kBigMaxB];
   unsigned long long pf_tot[kBigMaxB];
@@ -51,11 +53,22 @@ struct BigSmem {
   float usum, rsum;
   int csum, ncon;
   // inputs of the observation rows, published by the threads that own the UEs
-  float2 pxy[kBigMaxU];   // position after the move
-  uint2 cw[kBigMaxU];     // connection mask words
-  float ut[kBigMaxU];     // own-utility column
-  uint8_t ucls[kBigMaxU]; // UE class
+  float2 pxy[MAXU];   // position after the move
+  uint2 cw[MAXU];     // connection mask words
+  float ut[MAXU];     // own-utility column
+  uint8_t ucls[MAXU]; // UE class
 };
+
+// dynamic shared memory of the kernel: the struct above sized for MAXI UEs per thread, then (128-byte
+// aligned) one row tile per warp
+template <int MAXI>
+__host__ __device__ constexpr size_t big_tile_offset() {
+  return (sizeof(BigSmemT<MAXI * kBigThreads>) + 127) & ~(size_t)127;
+}
+template <int MAXI>
+__host__ __device__ constexpr size_t big_smem_bytes() {
+  return big_tile_offset<MAXI>() + (size_t)kBigTileFloats * 4 * kBigWarps;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -99,6 +112,7 @@ __global__ void __launch_bounds__(kBigThreads, MAXI <= 2 ? MBE_BIG_MIN_BLOCKS + 
   constexpr bool GYM = (MODE == 1);
   constexpr bool MA = (HANDLER == 1);
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  using BigSmem = BigSmemT<MAXI * kBigThreads>;
   BigSmem& s = *reinterpret_cast<BigSmem*>(smem_raw);
   const int U = a.U, B = a.B, F = a.F, MW = (B + 31) >> 5;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -470,21 +484,20 @@ __global__ void __launch_bounds__(kBigThreads, MAXI <= 2 ? MBE_BIG_MIN_BLOCKS + 
     }
     __syncthreads();
 
-#if MBE_BIG_ROW_INTERLEAVE
-    const int rstep = kBigWarps;
-    const int r0 = warp, r1 = U;
-#else
-    const int rstep = 1;
-    const int rpw = (U + kBigWarps - 1) / kBigWarps;  // rows per warp (contiguous: write locality)
-    const int r0 = warp * rpw, r1 = min(U, r0 + rpw);
-#endif
+    // Rows leave through shared memory: a warp fills a tile of TR whole rows (a multiple of 4 rows is a
+    // multiple of 16 bytes; with U % 4 == 0 every tile is also 16-byte aligned in global memory) and sends
+    // it as ONE bulk async copy.  The rows are 4F bytes with F odd, so direct 128-byte segment stores from
+    // registers start at every 4-byte phase of a 32-byte sector: profiles/row_store_bench.cu measures
+    // 3.5 TB/s for that pattern against 7.1-7.3 TB/s for the same rows as aligned bulk tiles.  Shapes
+    // whose rows cannot be tiled that way (U % 4 != 0, unaligned obs) keep the direct stores.
+    const bool tiled = a.obs_bulk_ok && (U % 4 == 0) && F <= kBigTileFloats / 4;
+    const int rpw = tiled ? (((U + kBigWarps - 1) / kBigWarps + 3) & ~3) : (U + kBigWarps - 1) / kBigWarps;
+    const int r0 = min(U, warp * rpw), r1 = min(U, r0 + rpw);  // rows of this warp (contiguous)
+    const int TR = tiled ? min(16, (kBigTileFloats / F) & ~3) : max(1, r1 - r0);
+    float* const tile = reinterpret_cast<float*>(smem_raw + big_tile_offset<MAXI>()) + (size_t)warp * kBigTileFloats;
     float* obase = a.obs + (size_t)env * U * F;
     if (done && !fresh) {  // inactive UEs observe zeros
-#if MBE_BIG_ROW_INTERLEAVE
-      for (size_t e = (size_t)tid; e < (size_t)U * F; e += kBigThreads) obase[e] = 0.0f;
-#else
       for (size_t e = (size_t)r0 * F + lane; e < (size_t)r1 * F; e += 32) obase[e] = 0.0f;
-#endif
       return;
     }
     const int b0 = lane, b1 = lane + 32;
@@ -501,14 +514,15 @@ __global__ void __launch_bounds__(kBigThreads, MAXI <= 2 ? MBE_BIG_MIN_BLOCKS + 
     }
     // FULL = both column groups exist for every lane (B == 64, the synthetic scale-up) and one link
     // class: no column predicates, the row's stores are one base pointer plus immediates
-    auto rows = [&](auto full_tag) {
+    // rows [u_lo, u_hi) into `dst` (row u_lo first, stride F): the global block or a shared-memory tile
+    auto rows = [&](auto full_tag, int u_lo, int u_hi, float* dst, bool with_util) {
       constexpr bool FULL = decltype(full_tag)::value;
       const int BB = FULL ? 64 : B;
 #pragma unroll 2
-      for (int u = r0; u < r1; u += rstep) {
+      for (int u = u_lo; u < u_hi; ++u) {
         const float2 p = s.pxy[u];
         const uint2 cw = s.cw[u];
-        float* row = obase + (size_t)u * F;
+        float* row = dst + (size_t)(u - u_lo) * F;
         // log2 snr of this lane's two BSs (d = 0 is the reference's EPSILON, channels.py:8: the 1e-32
         // vanishes in the rounding of every d2 >= 1)
         float dx = p.x - q0.x, dy = p.y - q0.y;
@@ -557,12 +571,33 @@ __global__ void __launch_bounds__(kBigThreads, MAXI <= 2 ? MBE_BIG_MIN_BLOCKS + 
           }
         }
       }
+      // the utility column (one element per row, stride F): up to 32 rows per store instruction
+      // instead of a predicated single-lane store in every row
+      if (with_util)
+        for (int u = u_lo + lane; u < u_hi; u += 32) dst[(size_t)(u - u_lo) * F + 2 * B] = s.ut[u];
     };
-    if (B == 64 && one_class) rows(std::true_type{});
-    else rows(std::false_type{});
-    // the utility column (one element per row, stride F): 32 rows per store instruction instead of a
-    // predicated single-lane store in every row
-    for (int u = r0 + lane * rstep; u < r1; u += 32 * rstep) obase[(size_t)u * F + 2 * B] = s.ut[u];
+    const bool full = B == 64 && one_class;
+    if (!tiled) {
+      if (full) rows(std::true_type{}, r0, r1, obase + (size_t)r0 * F, true);
+      else rows(std::false_type{}, r0, r1, obase + (size_t)r0 * F, true);
+      return;
+    }
+    for (int t0 = r0; t0 < r1; t0 += TR) {
+      const int t1 = min(r1, t0 + TR);
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous tile has been read
+      __syncwarp();
+      if (full) rows(std::true_type{}, t0, t1, tile, true);
+      else rows(std::false_type{}, t0, t1, tile, true);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(obase + (size_t)t0 * F),
+                     "r"((uint32_t)__cvta_generic_to_shared(tile)), "r"((uint32_t)((t1 - t0) * F) * 4u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   };
 
   // ================= run =================
