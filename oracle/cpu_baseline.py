@@ -1,8 +1,9 @@
-"""TEST/BENCH INFRASTRUCTURE ONLY -- times the CPU restatement of the reference's step on host
-cores (``cpu_baseline`` and ``--impl reference`` legs of bench.py).  The scalar port
-(``ScalarEnv``) runs per-entity Python loops exactly like the reference does
-(mobile_env/core/base.py:230-296), so its speed is the reference's speed class; the numbers it
-produces are a reported baseline, not a target."""
+"""TEST/BENCH INFRASTRUCTURE ONLY -- times the reference's step on host cores (``cpu_baseline`` and
+``--impl reference`` legs of bench.py): the UNMODIFIED reference where it is installed (``oracle/_ref``,
+built by ``oracle/build_ref.py``; kind "reference"), the oracle's scalar port (``ScalarEnv``: per-entity
+Python loops exactly like mobile_env/core/base.py:230-296, the reference's speed class; kind "port") and
+the compiled C restatement (``oracle/mbe_oracle_c.c``, OpenMP).  The numbers are reported baselines, not
+targets."""
 from __future__ import annotations
 
 import multiprocessing as mp
