@@ -209,7 +209,10 @@ __device__ __forceinline__ void step_chunk(const StepArgs& a, const int env_base
     int csum_i = 0;
 #pragma unroll
     for (int b = 0; b < B; ++b) {
-      cnt[b] = __popc(__ballot_sync(kFull, (conn >> b) & 1u) & segmask);
+      if constexpr (EPW == 1)  // the env is the whole warp (idle lanes hold conn = 0): one warp-wide integer add
+        cnt[b] = (int)__reduce_add_sync(kFull, (conn >> b) & 1u);
+      else
+        cnt[b] = __popc(__ballot_sync(kFull, (conn >> b) & 1u) & segmask);
       csum_i += cnt[b];
     }
     double rate = 0.0;
